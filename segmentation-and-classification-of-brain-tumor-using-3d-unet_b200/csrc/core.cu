@@ -1,0 +1,76 @@
+// core.cu — library-wide plumbing: last-error string, device query, TMA descriptor encode via the driver entry point.
+#include "b3d_common.cuh"
+#include "b3d_internal.h"
+#include <stdarg.h>
+#include <mutex>
+
+static thread_local char g_err[1024] = "";
+
+void b3d_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int b3d_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+int b3d_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = (EncodeTiledFn)fn;
+  });
+  if (!g_encode) {
+    b3d_set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return B3D_ERR_DRIVER;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b3d_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu %llu box %u %u %u %u %u base %p",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+                  rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0, base);
+    return B3D_ERR_DRIVER;
+  }
+  return B3D_OK;
+}
+
+extern "C" {
+const char* b3d_last_error_string() { return g_err; }
+int b3d_version() { return 100; }
+// 0 if the current device is sm_100 (B200); negative otherwise — callers must fail loudly, there is no fallback.
+int b3d_check_device() {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { b3d_set_error("no CUDA device"); return B3D_ERR_CUDA; }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) { b3d_set_error("device is sm_%d%d, libb3d is built for sm_100a only", major, minor); return B3D_ERR_UNSUPPORTED; }
+  return B3D_OK;
+}
+}
