@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
               }
               s1 = warp_sum(s1); s2 = warp_sum(s2);
               if (lane == 0) {
-                const int g = (j0 + sg) / P.cpg;  // group index local to this n-block
+                const int g = (n0 + j0 + sg) / P.cpg - n0 / P.cpg;  // group slot local to this n-block
                 atomicAdd(&s_stats[2 * g], s1);
                 atomicAdd(&s_stats[2 * g + 1], s2);
               }
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       if (lane == 0) mbar_arrive(tempty0 + 8 * a);
       if (P.stats != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int groups_blk = P.BN / P.cpg;
+        const int groups_blk = (n0 + P.BN - 1) / P.cpg - n0 / P.cpg + 1;
         if (et < 2 * groups_blk) {
           const int g = n0 / P.cpg + (et >> 1);
           if (g < P.stats_groups) {
@@ -392,7 +392,8 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
   const int halo = ks / 2, ntaps = ks * ks * ks;
   const int Ktotal = chan_per_map * nmaps;
   IgemmPlan best; best.ok = false; best.cost = 1e30;
-  const int bn_cands[5] = {CoutPad <= 256 ? CoutPad : 256, 256, 128, 64, 32};
+  const int bn_top = (mode == 2) ? std::min(CoutPad / 8, 256) : (CoutPad <= 256 ? CoutPad : 256);
+  const int bn_cands[6] = {bn_top, 256, 128, 64, 32, 16};
   const int env_td = getenv("B3D_TD") ? atoi(getenv("B3D_TD")) : 0;
   const int env_th = getenv("B3D_TH") ? atoi(getenv("B3D_TH")) : 0;
   const int env_kc = getenv("B3D_KC") ? atoi(getenv("B3D_KC")) : 0;
@@ -402,7 +403,7 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
   for (int TD = 1; TD <= 16 && TD <= D; TD *= 2)
     for (int TH = 1; TH <= 64 && TH <= H; TH *= 2)
       for (int KC = 64; KC >= 16; KC /= 2)
-        for (int bi = 0; bi < 5; ++bi) {
+        for (int bi = 0; bi < 6; ++bi) {
           const int BN = bn_cands[bi];
           if (bi > 0 && (BN >= bn_cands[0])) continue;
           if (BN > 256 || BN % 16) continue;
@@ -491,7 +492,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
                   CoutPad, ks);
     return B3D_ERR_UNSUPPORTED;
   }
-  if (stats) B3D_REQUIRE(pl.BN / cpg <= 32 && pl.BN % cpg == 0, "igemm: BN %d / cpg %d unsupported", pl.BN, cpg);
+  if (stats) B3D_REQUIRE(pl.BN / cpg <= 32 && (pl.BN % cpg == 0 || cpg % pl.BN == 0), "igemm: BN %d / cpg %d unsupported", pl.BN, cpg);
 
   IgemmParams P;
   memset(&P, 0, sizeof(P));
