@@ -1,0 +1,510 @@
+// conv_wgrad.cu — weight gradients of the 3-D convolutions on tcgen05 tensor cores (sm_100a).
+//
+//   dW[tap][ci][co] = Σ_{n,z,y,x} X[n, z+kd-1, y+kh-1, x+kw-1][ci] * dY[n,z,y,x][co]
+// (what autograd's convolution_backward computes for nn.Conv3d / nn.ConvTranspose3d in /root/reference/main.py:121,130,
+//  216,219,229,252,258 — 52 % of the reference's CPU step time).
+//
+// GEMM view: D[M = input channels (x stacked taps)][N = output channels] += A[M][K] * B[K][N] with K = voxels.
+// Both operands are "MN-major" for the UMMA (the contracted index, voxels, is the slow one in NDHWC), staged by TMA as
+//     X  slot : [row][8-channel chunk][x position][8 ch = 16 B]          (box (8, BW, CI8, BH, 1) of a 5-D view whose
+//     dY slot : [row][8-channel chunk][x position][8 ch = 16 B]           chunk dimension has a 16-byte stride)
+// so that  * a K=16 step is 16 consecutive x positions of one row (LBO = 128 B),
+//          * the next 8-channel chunk is SBO = BW*16 B away, and — because chunks of consecutive ROWS are also SBO
+//            apart — M = 128 can hold G = 128/ci_blk vertically shifted copies of the tile: for Cin <= 32 the three kh
+//            taps are STACKED on M (rows y, y+1, y+2 (+1 unused)), which fills the 128-row tensor-core tile that a 32-wide
+//            channel block alone would leave 75 % empty,
+//          * kw shifts are +16 B on the A start address, kd shifts select another X plane of a 3-deep rolling ring.
+// Accumulators (one [128 x BN] fp32 tile per (kd,kw) chain) stay in TMEM across ALL tiles a CTA processes for the same
+// output block and are flushed once with fp32 atomics into dwacc[tap][ci][co]; wgrad_finalize permutes into the
+// reference's [co][ci][kd][kh][kw] layout.
+// "Plane mode" (W not a multiple of 16: the 8^3 / 4^3 levels) linearises a whole halo plane as the K run instead of rows.
+#include "b3d_common.cuh"
+#include "b3d_internal.h"
+#include <algorithm>
+
+struct alignas(64) WgradParams {
+  CUtensorMap tmX;
+  CUtensorMap tmY[8];
+  int variant;      // 0: kh stacked on M, 9 (kd,kw) chains ; 1: key=(kd,kh), 3 kw chains ; 2: pointwise, 1 chain
+  int plane_mode;   // 0: K runs along rows ; 1: K runs along a linearised halo plane
+  int N, D, H, W, halo;
+  int TH, BH, BW, TZ;
+  int ci_blk, CI8, G, BN, CO8, n_cib, n_cob, nmapsY;
+  int nchains, xspan, R;
+  uint32_t x_slot_bytes, y_slot_bytes, x_tx_bytes, y_tx_bytes;
+  int XP, YP;       // plane mode: padded positions per chunk in the X / dY slot
+  int ksteps;
+  int tiles_y, tiles_z, items_per_key, num_keys, num_items, items_per_cta;
+  float* dwacc;
+  int Cin, Cout, Cout_pad, Cin_pad;
+  int tmem_cols;
+  int* err;
+};
+
+#define WG_THREADS 192
+
+struct KeyInfo { int cib, cob, kd, kh, t8; };
+
+__device__ __forceinline__ KeyInfo decode_key(const WgradParams& P, int key) {
+  KeyInfo k; k.kd = -1; k.kh = -1; k.t8 = 0;
+  if (P.variant == 0) { k.cob = key % P.n_cob; k.cib = key / P.n_cob; }
+  else if (P.variant == 1) { k.kh = key % 3; key /= 3; k.kd = key % 3; key /= 3; k.cob = key % P.n_cob; k.cib = key / P.n_cob; }
+  else { k.t8 = key % P.nmapsY; key /= P.nmapsY; k.cob = key % P.n_cob; k.cib = key / P.n_cob; }
+  return k;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sX = smem_u32(smem);
+  const uint32_t sY = sX + P.R * P.x_slot_bytes;
+  const uint32_t y_end = sY + 2 * P.y_slot_bytes;
+  // aux region sits after a guard gap (garbage M rows may read past the last slot)
+  const uint32_t aux_off = (uint32_t)(P.R * P.x_slot_bytes + 2 * P.y_slot_bytes);
+  uint8_t* aux = smem + aux_off;
+  const uint32_t xfull0 = smem_u32(aux);            // [R]
+  const uint32_t xempty0 = xfull0 + 8 * 4;          // [R] (R <= 4)
+  const uint32_t yfull0 = xempty0 + 8 * 4;          // [2]
+  const uint32_t yempty0 = yfull0 + 16;             // [2]
+  const uint32_t accfull = yempty0 + 16;
+  const uint32_t accempty = accfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 8 * 4 * 2 + 32 + 16);
+  (void)y_end;
+
+  if (threadIdx.x == 0) {
+    if (sX & 127u) { if (P.err) atomicExch(P.err, 19); __trap(); }
+    for (int i = 0; i < 4; ++i) { mbar_init(xfull0 + 8 * i, 1); mbar_init(xempty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(yfull0 + 8 * i, 1); mbar_init(yempty0 + 8 * i, 1); }
+    mbar_init(accfull, 1); mbar_init(accempty, 4);
+    mbar_fence_init();
+  }
+  if (P.plane_mode) {
+    // zero the staging slots once: tails beyond the TMA boxes are read as K elements and must be finite zeros
+    uint4* p = reinterpret_cast<uint4*>(smem);
+    const uint32_t n16 = aux_off / 16;
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), P.tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int item_beg = blockIdx.x * P.items_per_cta;
+  const int item_end = min(P.num_items, item_beg + P.items_per_cta);
+  const int zoff0 = (P.variant == 0) ? -P.halo : 0;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      tma_prefetch_desc(&P.tmX);
+      uint32_t Q = 0, T = 0;  // running X-plane / dY-plane fill counters
+      for (int item = item_beg; item < item_end; ++item) {
+        const int key = item / P.items_per_key;
+        int r = item - key * P.items_per_key;
+        const KeyInfo k = decode_key(P, key);
+        const int ty = r % P.tiles_y; r /= P.tiles_y;
+        const int tz = r % P.tiles_z; const int n = r / P.tiles_z;
+        const int y0 = ty * P.TH, z0 = tz * P.TZ;
+        const int nz = min(P.TZ, P.D - z0);
+        const int zoff = (P.variant == 1) ? (k.kd - 1) : zoff0;
+        const int yoff = P.plane_mode ? -P.halo : ((P.variant == 0) ? -P.halo : (P.variant == 1 ? k.kh - 1 : 0));
+        const int nplanes = nz + P.xspan - 1;
+        for (int s = 0; s < nplanes; ++s) {
+          {  // X plane s
+            const uint32_t slot = Q % P.R, ph = (Q / P.R) & 1u;
+            mbar_wait(xempty0 + 8 * slot, ph ^ 1, P.err, 11);
+            const int z = z0 + s + zoff;
+            const uint32_t fb = xfull0 + 8 * slot;
+            if (z >= 0 && z < P.D) {
+              mbar_expect_tx(fb, P.x_tx_bytes);
+              if (P.plane_mode) {
+                for (int c8 = 0; c8 < P.CI8; ++c8)  // one box per chunk: chunks sit at the padded pitch XP
+                  tma_load_5d(sX + slot * P.x_slot_bytes + c8 * P.XP * 16, &P.tmX, fb, 0, -P.halo, y0 + yoff,
+                              k.cib * P.CI8 + c8, n * P.D + z);
+              } else
+                tma_load_5d(sX + slot * P.x_slot_bytes, &P.tmX, fb, 0, -P.halo, k.cib * P.CI8, y0 + yoff, n * P.D + z);
+            } else {
+              mbar_arrive(fb);  // out-of-volume plane: nothing to load, the consumer skips it
+            }
+            ++Q;
+          }
+          if (s >= P.xspan - 1) {  // dY plane t
+            const int t = s - (P.xspan - 1);
+            const uint32_t slot = T & 1u, ph = (T >> 1) & 1u;
+            mbar_wait(yempty0 + 8 * slot, ph ^ 1, P.err, 12);
+            const uint32_t fb = yfull0 + 8 * slot;
+            mbar_expect_tx(fb, P.y_tx_bytes);
+            if (P.plane_mode) {
+              for (int c8 = 0; c8 < P.CO8; ++c8)
+                tma_load_5d(sY + slot * P.y_slot_bytes + c8 * P.YP * 16, &P.tmY[k.t8], fb, 0, 0, y0, k.cob * P.CO8 + c8,
+                            n * P.D + z0 + t);
+            } else
+              tma_load_5d(sY + slot * P.y_slot_bytes, &P.tmY[k.t8], fb, 0, 0, k.cob * P.CO8, y0, n * P.D + z0 + t);
+            ++T;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, P.BN, 1, 1);
+      const uint32_t lbo = (128u >> 4) << 16;
+      const uint64_t hiA = umma_desc_hi(P.plane_mode ? (uint32_t)P.XP * 16u : (uint32_t)P.BW * 16u);
+      const uint64_t hiB = umma_desc_hi(P.plane_mode ? (uint32_t)P.YP * 16u : (uint32_t)P.W * 16u);
+      uint32_t Q = 0, T = 0, started = 0, flushes = 0;
+      int cur_key = -1;
+      for (int item = item_beg; item < item_end; ++item) {
+        const int key = item / P.items_per_key;
+        int r = item - key * P.items_per_key;
+        const KeyInfo k = decode_key(P, key);
+        const int ty = r % P.tiles_y; r /= P.tiles_y;
+        const int tz = r % P.tiles_z;
+        const int y0 = ty * P.TH, z0 = tz * P.TZ;
+        const int nz = min(P.TZ, P.D - z0);
+        const int rows = min(P.TH, P.H - y0);
+        if (key != cur_key) {
+          if (cur_key >= 0) {
+            umma_commit(accfull);
+            mbar_wait(accempty, flushes & 1u, P.err, 13);
+            tc_fence_after();
+            ++flushes;
+          }
+          cur_key = key; started = 0;
+        }
+        const int zoff = (P.variant == 1) ? (k.kd - 1) : zoff0;
+        const uint32_t Q0 = Q;
+        for (int t = 0; t < nz; ++t) {
+          const uint32_t yslot = T & 1u, yph = (T >> 1) & 1u;
+          mbar_wait(yfull0 + 8 * yslot, yph, P.err, 14);
+          const uint32_t yb16 = (sY + yslot * P.y_slot_bytes) >> 4;
+          for (int a = 0; a < P.xspan; ++a) {  // a = kd for variant 0
+            const uint32_t q = Q0 + t + a;
+            const uint32_t xslot = q % P.R, xph = (q / P.R) & 1u;
+            mbar_wait(xfull0 + 8 * xslot, xph, P.err, 15);
+            tc_fence_after();
+            const int z = z0 + t + a + zoff;
+            if (z >= 0 && z < P.D) {
+              const uint32_t xb16 = (sX + xslot * P.x_slot_bytes) >> 4;
+              const int nkw = (P.halo ? 3 : 1);
+              if (!P.plane_mode) {
+                for (int y = 0; y < rows; ++y) {
+                  const uint32_t arow = xb16 + (uint32_t)(y * P.CI8) * P.BW;
+                  const uint32_t brow = yb16 + (uint32_t)(y * P.CO8) * P.W;
+                  for (int j = 0; j < P.ksteps; ++j) {
+                    const uint32_t blo = ((brow + j * 16) & 0x3FFFu) | lbo;
+                    for (int kw = 0; kw < nkw; ++kw) {
+                      const int chain = (P.variant == 0) ? a * 3 + kw : kw;
+                      const uint32_t alo = ((arow + j * 16 + kw) & 0x3FFFu) | lbo;
+                      umma_bf16_ss(tmem_base + chain * P.BN, hiA | alo, hiB | blo, idesc, (started >> chain) & 1u);
+                      started |= 1u << chain;
+                    }
+                  }
+                }
+              } else {
+                const int khoff = (P.variant == 1) ? k.kh * P.BW : 0;
+                for (int j = 0; j < P.ksteps; ++j) {
+                  const uint32_t blo = ((yb16 + j * 16) & 0x3FFFu) | lbo;
+                  for (int kw = 0; kw < nkw; ++kw) {
+                    const uint32_t alo = ((xb16 + j * 16 + khoff + kw) & 0x3FFFu) | lbo;
+                    umma_bf16_ss(tmem_base + kw * P.BN, hiA | alo, hiB | blo, idesc, (started >> kw) & 1u);
+                    started |= 1u << kw;
+                  }
+                }
+              }
+            }
+            if (a == 0) umma_commit(xempty0 + 8 * xslot);  // plane t (+zoff) is not needed by later output planes
+          }
+          umma_commit(yempty0 + 8 * yslot);
+          ++T;
+        }
+        // planes nz .. nz+xspan-2 of this item were only partially consumed: release them
+        for (int a = 1; a < P.xspan; ++a) {
+          const uint32_t q = Q0 + nz - 1 + a;
+          umma_commit(xempty0 + 8 * (q % P.R));
+        }
+        Q = Q0 + nz + P.xspan - 1;
+      }
+      if (cur_key >= 0) umma_commit(accfull);
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue: flush TMEM accumulators with fp32 atomics =======================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int cur_key = -1;
+    uint32_t flushes = 0;
+    for (int item = item_beg; item <= item_end; ++item) {
+      const int key = (item < item_end) ? item / P.items_per_key : -2;
+      if (key == cur_key) continue;
+      if (cur_key >= 0) {
+        mbar_wait(accfull, flushes & 1u, P.err, 16);
+        tc_fence_after();
+        const KeyInfo k = decode_key(P, cur_key);
+        const int khs = m / P.ci_blk;
+        const int ci = k.cib * P.ci_blk + (m - khs * P.ci_blk);
+        int kh = 0;
+        bool row_ok = ci < P.Cin;
+        if (P.variant == 0) { kh = khs; row_ok = row_ok && (kh < 3); }
+        else { kh = k.kh; row_ok = row_ok && (khs == 0); }
+        for (int chain = 0; chain < P.nchains; ++chain) {
+          int tap;
+          if (P.variant == 0) tap = ((chain / 3) * 3 + kh) * 3 + (chain % 3);
+          else if (P.variant == 1) tap = (k.kd * 3 + kh) * 3 + chain;
+          else tap = k.t8;
+          float* dst = P.dwacc + ((long long)tap * P.Cin_pad + ci) * P.Cout_pad + k.cob * P.BN;
+          const uint32_t trow = tmem_base + chain * P.BN + ((uint32_t)(q * 32) << 16);
+          for (int j0 = 0; j0 < P.BN; j0 += 16) {
+            uint32_t rr[16];
+            tmem_ld16(trow + j0, rr);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (k.cob * P.BN + j0 + j < P.Cout_pad) atomicAdd(dst + j0 + j, __uint_as_float(rr[j]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accempty);
+        ++flushes;
+      }
+      cur_key = key;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, P.tmem_cols); }
+}
+
+// dwacc fp32 [taps][Cin_pad][Cout_pad] -> reference layouts (fp32), optionally accumulating into an existing gradient
+//   mode 0: conv   dW[co][ci][tap]           mode 1: convT  dWt[ci][co][t8]
+__global__ void wgrad_finalize_kernel(const float* __restrict__ acc, float* __restrict__ dw, int mode, int ntaps, int Cin,
+                                      int Cout, int Cin_pad, int Cout_pad, int accumulate) {
+  const long long total = (long long)ntaps * Cin * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    int tap, ci, co;
+    if (mode == 0) { tap = (int)(t % ntaps); t /= ntaps; ci = (int)(t % Cin); co = (int)(t / Cin); }
+    else { tap = (int)(t % ntaps); t /= ntaps; co = (int)(t % Cout); ci = (int)(t / Cout); }
+    const float v = acc[((long long)tap * Cin_pad + ci) * Cout_pad + co];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static const int kWgSmemBudget = 227 * 1024 - 1024;
+static bool g_wg_attr = false;
+
+struct YView { const void* base; long long sW, sH, sND; };
+
+static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv, int nmapsY, int N, int D, int H, int W,
+                     int Cout, int ks, float* dwacc, int Cin_pad, int Cout_pad, int* err_flag, cudaStream_t stream) {
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  const int halo = ks / 2;
+  const int num_sms = b3d_num_sms();
+  B3D_REQUIRE(Cin_use % 8 == 0 && Cout % 8 == 0, "wgrad: channels must be multiples of 8");
+  P.N = N; P.D = D; P.H = H; P.W = W; P.halo = halo;
+  P.Cin = Cin_use; P.Cout = Cout; P.Cin_pad = Cin_pad; P.Cout_pad = Cout_pad; P.nmapsY = nmapsY;
+  P.plane_mode = (W % 16 != 0) ? 1 : 0;
+  P.BW = W + 2 * halo;
+  B3D_REQUIRE(P.BW <= 256, "wgrad: W=%d too wide for one TMA box", W);
+  if (ks == 3 && !P.plane_mode && Cin_use <= 64) {
+    P.variant = 0; P.ci_blk = std::min(Cin_use, 32); P.G = 128 / P.ci_blk; P.nchains = 9; P.xspan = 3; P.R = 3;
+    P.BN = (Cout_pad % 48 == 0) ? 48 : (Cout_pad >= 32 ? 32 : 16);
+  } else if (ks == 3) {
+    P.variant = 1; P.ci_blk = std::min(Cin_use, 128); P.G = 1; P.nchains = 3; P.xspan = 1; P.R = 2;
+    P.BN = std::min(Cout_pad, 128);
+  } else {
+    P.variant = 2; P.ci_blk = std::min(Cin_use, 128); P.G = 1; P.nchains = 1; P.xspan = 1; P.R = 2;
+    P.BN = std::min(Cout_pad, 256);
+  }
+  B3D_REQUIRE(Cin_use % P.ci_blk == 0, "wgrad: Cin=%d not a multiple of the channel block %d", Cin_use, P.ci_blk);
+  P.CI8 = P.ci_blk / 8; P.CO8 = P.BN / 8;
+  P.n_cib = Cin_use / P.ci_blk; P.n_cob = (Cout_pad + P.BN - 1) / P.BN;
+  B3D_REQUIRE(P.BN % 16 == 0 && Cout_pad % 16 == 0, "wgrad: Cout_pad must be a multiple of 16");
+  int cols = P.nchains * P.BN, tc = 32;
+  while (tc < cols) tc *= 2;
+  P.tmem_cols = tc;
+  B3D_REQUIRE(tc <= 512, "wgrad: TMEM overflow");
+
+  // tile rows
+  int TH;
+  if (P.plane_mode) {
+    TH = H;
+    const int BH = H + 2 * halo;
+    P.BH = BH;
+    P.ksteps = ((H - 1) * P.BW + W + 15) / 16;
+    const int maxpos = P.ksteps * 16 + (P.halo ? 2 * P.BW + 2 : 0);
+    P.XP = (std::max(BH * P.BW, maxpos) + 7) / 8 * 8;
+    P.YP = (std::max(H * P.BW, P.ksteps * 16) + 7) / 8 * 8;
+    // one TMA box per 8-channel chunk, landing at the padded pitch (XP / YP positions); the pads stay zero
+    P.x_slot_bytes = (uint32_t)(((long long)P.CI8 * P.XP * 16 + 1023) / 1024 * 1024);
+    P.y_slot_bytes = (uint32_t)(((long long)P.CO8 * P.YP * 16 + 1023) / 1024 * 1024);
+    P.x_tx_bytes = (uint32_t)P.CI8 * BH * P.BW * 16;
+    P.y_tx_bytes = (uint32_t)P.CO8 * H * P.BW * 16;
+    B3D_REQUIRE(BH <= 256 && P.CI8 <= 256, "wgrad: plane too large");
+  } else {
+    TH = 1;
+    for (int cand = 16; cand >= 1; cand /= 2) {
+      if (cand > H && cand > 1) continue;
+      const int BH = (P.variant == 0) ? cand + 2 : cand;
+      const long long xs = ((long long)BH * P.CI8 * P.BW * 16 + 1023) / 1024 * 1024;
+      const long long ys = ((long long)cand * P.CO8 * W * 16 + 1023) / 1024 * 1024;
+      const long long guard = (long long)16 * P.BW * 16 * 2 + 4096;
+      if (P.R * xs + 2 * ys + guard + 256 <= kWgSmemBudget) { TH = cand; break; }
+    }
+    P.BH = (P.variant == 0) ? TH + 2 : TH;
+    P.ksteps = W / 16;
+    P.x_slot_bytes = (uint32_t)(((long long)P.BH * P.CI8 * P.BW * 16 + 1023) / 1024 * 1024);
+    P.y_slot_bytes = (uint32_t)(((long long)TH * P.CO8 * W * 16 + 1023) / 1024 * 1024);
+    P.x_tx_bytes = (uint32_t)P.BH * P.CI8 * P.BW * 16;
+    P.y_tx_bytes = (uint32_t)TH * P.CO8 * W * 16;
+    B3D_REQUIRE(P.BH <= 256, "wgrad: tile too tall");
+  }
+  P.TH = TH;
+  P.tiles_y = (H + TH - 1) / TH;
+  if (P.variant == 0) P.num_keys = P.n_cib * P.n_cob;
+  else if (P.variant == 1) P.num_keys = P.n_cib * P.n_cob * 9;
+  else P.num_keys = P.n_cib * P.n_cob * nmapsY;
+  int TZ = D;
+  while (TZ > 4 && (long long)P.num_keys * N * P.tiles_y * ((D + TZ - 1) / TZ) < 2LL * num_sms) TZ /= 2;
+  if (TZ < 1) TZ = 1;
+  P.TZ = TZ;
+  P.tiles_z = (D + TZ - 1) / TZ;
+  P.items_per_key = N * P.tiles_y * P.tiles_z;
+  P.num_items = P.items_per_key * P.num_keys;
+  const int grid = std::min(P.num_items, num_sms);
+  P.items_per_cta = (P.num_items + grid - 1) / grid;
+  const int grid2 = (P.num_items + P.items_per_cta - 1) / P.items_per_cta;
+  P.dwacc = dwacc; P.err = err_flag;
+
+  // guard: garbage M rows (16 chunks x SBO) may read beyond the last slot; keep it inside the allocation
+  const long long sbo_a = P.plane_mode ? (long long)P.XP * 16 : (long long)P.BW * 16;
+  const long long guard = 16 * sbo_a + 4096;
+  const size_t smem = (size_t)P.R * P.x_slot_bytes + 2 * (size_t)P.y_slot_bytes + 256 + (size_t)guard;
+  B3D_REQUIRE(smem <= 227 * 1024, "wgrad: smem %zu too large (N%d D%d H%d W%d Cin%d Cout%d ks%d)", smem, N, D, H, W, Cin_use,
+              Cout, ks);
+
+  const int C8tot = Cin_use / 8;
+  {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    const uint64_t sW = (uint64_t)ldx * 2, sH = sW * W, sND = sH * H;
+    if (P.plane_mode) {
+      dims[0] = 8; dims[1] = W; dims[2] = H; dims[3] = C8tot; dims[4] = (uint64_t)N * D;
+      strides[0] = sW; strides[1] = sH; strides[2] = 16; strides[3] = sND;
+      box[0] = 8; box[1] = P.BW; box[2] = P.BH; box[3] = 1; box[4] = 1;
+    } else {
+      dims[0] = 8; dims[1] = W; dims[2] = C8tot; dims[3] = H; dims[4] = (uint64_t)N * D;
+      strides[0] = sW; strides[1] = 16; strides[2] = sH; strides[3] = sND;
+      box[0] = 8; box[1] = P.BW; box[2] = P.CI8; box[3] = P.BH; box[4] = 1;
+    }
+    int rc = b3d_encode_tmap_bf16(&P.tmX, x, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int m = 0; m < nmapsY; ++m) {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    const int C8o = Cout_pad / 8;
+    if (P.plane_mode) {
+      dims[0] = 8; dims[1] = W; dims[2] = H; dims[3] = C8o; dims[4] = (uint64_t)N * D;
+      strides[0] = yv[m].sW; strides[1] = yv[m].sH; strides[2] = 16; strides[3] = yv[m].sND;
+      box[0] = 8; box[1] = P.BW; box[2] = H; box[3] = 1; box[4] = 1;
+    } else {
+      dims[0] = 8; dims[1] = W; dims[2] = C8o; dims[3] = H; dims[4] = (uint64_t)N * D;
+      strides[0] = yv[m].sW; strides[1] = 16; strides[2] = yv[m].sH; strides[3] = yv[m].sND;
+      box[0] = 8; box[1] = W; box[2] = P.CO8; box[3] = TH; box[4] = 1;
+    }
+    int rc = b3d_encode_tmap_bf16(&P.tmY[m], yv[m].base, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (!g_wg_attr) {
+    B3D_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_wg_attr = true;
+  }
+  if (getenv("B3D_VERBOSE"))
+    fprintf(stderr,
+            "[b3d] wgrad N%d D%d H%d W%d Cin%d Cout%d ks%d variant%d plane%d ci_blk%d G%d BN%d chains%d TH%d TZ%d keys%d "
+            "items%d (per cta %d) smem%zu tmem%d\n",
+            N, D, H, W, Cin_use, Cout, ks, P.variant, P.plane_mode, P.ci_blk, P.G, P.BN, P.nchains, P.TH, P.TZ, P.num_keys,
+            P.num_items, P.items_per_cta, smem, P.tmem_cols);
+  wgrad_kernel<<<grid2, WG_THREADS, smem, stream>>>(P);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+extern "C" {
+
+// Conv3d weight gradient.  x: [N,D,H,W,*] bf16 pitch ldx, first Cin channels used; dy: [N,D,H,W,Cout_pad>=Cout] pitch lddy.
+// dw: fp32 [Cout][Cin_real][ks^3] (reference layout).  ws: fp32 scratch of ks^3 * Cin_pad * Cout_pad floats.
+int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy, float* dw, int accumulate, int N, int D,
+                   int H, int W, int Cin, int Cin_real, int Cout, int ks, float* ws, size_t ws_bytes, int* err_flag,
+                   void* stream) {
+  B3D_REQUIRE(ks == 1 || ks == 3, "conv_wgrad: ks must be 1 or 3");
+  B3D_REQUIRE(Cin % 16 == 0 || Cin % 8 == 0, "conv_wgrad: Cin must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntaps = ks * ks * ks;
+  const int Cout_pad = (Cout + 15) / 16 * 16;
+  B3D_REQUIRE(lddy >= Cout_pad || Cout_pad == Cout, "conv_wgrad: dy must expose %d (padded) channels", Cout_pad);
+  const size_t need = (size_t)ntaps * Cin * Cout_pad * 4;
+  B3D_REQUIRE(ws_bytes >= need, "conv_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  B3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  int n = N, d = D, h = H, w = W;
+  if (ks == 1) {  // pointwise: flatten every voxel of the batch into rows of up to 128 positions
+    const long long V = (long long)N * D * H * W;
+    int ww = 128;
+    while (ww > 16 && V % ww) ww /= 2;
+    B3D_REQUIRE(V % ww == 0, "conv_wgrad: voxel count %lld not a multiple of 16", V);
+    n = 1; d = 1; w = ww; h = (int)(V / ww);
+    if (h > 65536) {  // keep TMA coordinates small: fold rows into planes
+      int dd = 1;
+      while (h > 4096 && h % 2 == 0) { h /= 2; dd *= 2; }
+      d = dd;
+    }
+  }
+  YView yv;
+  yv.base = dy; yv.sW = lddy * 2; yv.sH = yv.sW * w; yv.sND = yv.sH * h;
+  int rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
+  if (rc) return rc;
+  const long long total = (long long)ntaps * Cin_real * Cout;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// ConvTranspose3d(k=2,s=2) weight gradient: x [N,D,H,W,Cin] (coarse), dy [N,2D,2H,2W,Cout] -> dWt fp32 [Cin][Cout][8]
+int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long lddy, float* dw, int accumulate, int N, int D,
+                     int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int* err_flag, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cout_pad = (Cout + 15) / 16 * 16;
+  B3D_REQUIRE(Cout_pad == Cout, "convT2_wgrad: Cout must be a multiple of 16");
+  const size_t need = (size_t)8 * Cin * Cout_pad * 4;
+  B3D_REQUIRE(ws_bytes >= need, "convT2_wgrad: workspace too small");
+  B3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  YView yv[8];
+  const long long pW = lddy * 2, pH = pW * (2 * W), pD = pH * (2 * H);
+  for (int t8 = 0; t8 < 8; ++t8) {
+    const int a = t8 >> 2, b = (t8 >> 1) & 1, c = t8 & 1;
+    yv[t8].base = (const char*)dy + a * pD + b * pH + c * pW;
+    yv[t8].sW = 2 * pW; yv[t8].sH = 2 * pH; yv[t8].sND = 2 * pD;
+  }
+  // the N*D planes of the coarse grid: plane (n,z) of view t8 starts at n*(2D)*pD + 2z*pD = (n*D+z)*2*pD  -> uniform stride
+  int rc = run_wgrad(x, ldx, Cin, yv, 8, N, D, H, W, Cout, 1, ws, Cin, Cout_pad, err_flag, st);
+  if (rc) return rc;
+  const long long total = (long long)8 * Cin * Cout;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+}  // extern "C"

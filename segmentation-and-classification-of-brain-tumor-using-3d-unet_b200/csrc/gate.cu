@@ -1,0 +1,467 @@
+// gate.cu — AttentionGate3D (spatial attention + squeeze-excite channel attention), NDHWC bf16, HBM-bound kernels.
+//
+// Reference: /root/reference/main.py:244-299
+//     g1 = GN4(conv1(g)+bg) ; x1 = GN4(conv1(x)+bx)                       (the two 1x1 convs run on tcgen05: conv_igemm.cu,
+//     q  = relu(g1 + x1)                                                    their epilogues give the GN4 statistics)
+//     ψr = conv1(q; wψ)+bψ   [1 channel] ; ψ = sigmoid(GN(1,1)(ψr))        -> gate_psi_fwd (+ Σψr, Σψr² per sample)
+//     ca = sigmoid(W2·relu(W1·mean_v(x)+b1)+b2)                            -> channel_sum (pool_layout.cu) + gate_se_fwd
+//     out = x * ψ * ca                                                      -> gate_apply_fwd (writes the concat slice)
+// Backward follows SURVEY App. A2 with the same three global reductions.
+#include "b3d_common.cuh"
+#include "b3d_internal.h"
+#include <algorithm>
+
+static int gt_blocks_per_sample(long long work, int threads, int N) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = std::max(1, b3d_num_sms() * 8 / std::max(1, N));
+  return (int)std::max<long long>(1, std::min(b, cap));
+}
+
+__device__ __forceinline__ void mean_rstd_from(const double* st, double m, float eps, float& mean, float& rstd) {
+  const double mu = st[0] / m;
+  double var = st[1] / m - mu * mu;
+  if (var < 0) var = 0;
+  mean = (float)mu; rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ------------------------------------------------------------------------------------------------
+// ψr[n][v] = bψ + Σ_c wψ[c] * relu(GN4(g1r)[c] + GN4(x1r)[c]) ;  stats_psi[n] += (Σψr, Σψr²)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
+    const bf16* __restrict__ g1r, const bf16* __restrict__ x1r, const double* __restrict__ st_g,
+    const double* __restrict__ st_x, const float* __restrict__ gam_g, const float* __restrict__ bet_g,
+    const float* __restrict__ gam_x, const float* __restrict__ bet_x, const float* __restrict__ wpsi, float bpsi_unused,
+    const float* __restrict__ bpsi, float* __restrict__ psi_raw, double* __restrict__ st_psi, long long V, int F, float eps) {
+  extern __shared__ float sm[];
+  float* scg = sm; float* scx = sm + F; float* sh = sm + 2 * F; float* wp = sm + 3 * F;
+  __shared__ float s_red[2];
+  const int n = blockIdx.y;
+  const int cpg = F / 4;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float mg, rg, mx, rx;
+    mean_rstd_from(st_g + ((long long)n * 4 + c / cpg) * 2, (double)cpg * V, eps, mg, rg);
+    mean_rstd_from(st_x + ((long long)n * 4 + c / cpg) * 2, (double)cpg * V, eps, mx, rx);
+    const float a = gam_g[c] * rg, b = gam_x[c] * rx;
+    scg[c] = a; scx[c] = b; sh[c] = bet_g[c] - mg * a + bet_x[c] - mx * b; wp[c] = wpsi[c];
+  }
+  if (threadIdx.x < 2) s_red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const float bp = bpsi[0];
+  const int F8 = F >> 3;
+  const int lanes_c = F8 < 32 ? F8 : 32;
+  const int vpw = 32 / lanes_c;
+  const int lane = threadIdx.x & 31;
+  const int lc = lane % lanes_c, lv = lane / lanes_c;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bf16* gn_ = g1r + (long long)n * V * F;
+  const bf16* xn_ = x1r + (long long)n * V * F;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long v0 = warp_id * vpw; v0 < V; v0 += nwarps * vpw) {
+    const long long v = v0 + lv;
+    float acc = 0.f;
+    if (v < V) {
+      for (int c8 = lc; c8 < F8; c8 += lanes_c) {
+        float a[8], b[8];
+        unpack8(ldg16_stream(gn_ + v * F + c8 * 8), a);
+        unpack8(ldg16_stream(xn_ + v * F + c8 * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c8 * 8 + j;
+          const float q = fmaxf(fmaf(a[j], scg[c], fmaf(b[j], scx[c], sh[c])), 0.f);
+          acc = fmaf(q, wp[c], acc);
+        }
+      }
+    }
+    for (int o = lanes_c >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lc == 0 && v < V) {
+      const float p = acc + bp;
+      psi_raw[(long long)n * V + v] = p;
+      s1 += p; s2 += p * p;
+    }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { atomicAdd(&s_red[0], s1); atomicAdd(&s_red[1], s2); }
+  __syncthreads();
+  if (threadIdx.x < 2) atomicAdd(&st_psi[(long long)n * 2 + threadIdx.x], (double)s_red[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite: ca[n][c] = sigmoid(b2[c] + Σ_j W2[c][j] * relu(b1[j] + Σ_k W1[j][k] * mean[n][k]))
+// ------------------------------------------------------------------------------------------------
+__global__ void gate_se_fwd_kernel(const double* __restrict__ xsum, long long V, const float* __restrict__ w1,
+                                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                   float* __restrict__ ca, float* __restrict__ zbuf, float* __restrict__ meanbuf, int C) {
+  extern __shared__ float sm[];
+  float* mean = sm; float* z = sm + C;
+  const int n = blockIdx.x, R = C / 8;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    mean[c] = (float)(xsum[(long long)n * C + c] / (double)V);
+    meanbuf[(long long)n * C + c] = mean[c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    float a = b1[j];
+    for (int k = 0; k < C; ++k) a = fmaf(w1[(long long)j * C + k], mean[k], a);
+    z[j] = fmaxf(a, 0.f);
+    zbuf[(long long)n * R + j] = z[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int j = 0; j < R; ++j) a = fmaf(w2[(long long)c * R + j], z[j], a);
+    ca[(long long)n * C + c] = 1.f / (1.f + __expf(-a));
+  }
+}
+
+// out = x * sigmoid(GN1(ψr)) * ca
+__global__ void __launch_bounds__(256) gate_apply_fwd_kernel(const bf16* __restrict__ x, long long ldx,
+                                                             const float* __restrict__ psi_raw, const double* __restrict__ st_psi,
+                                                             const float* __restrict__ gpsi, const float* __restrict__ bpsi_n,
+                                                             const float* __restrict__ ca, bf16* __restrict__ out, long long ldo,
+                                                             long long V, int C, float eps) {
+  extern __shared__ float sca[];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sca[c] = ca[(long long)n * C + c];
+  float mu, rstd;
+  mean_rstd_from(st_psi + (long long)n * 2, (double)V, eps, mu, rstd);
+  const float a = gpsi[0] * rstd, b = bpsi_n[0] - mu * a;
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = V * C8;
+  const bf16* xn = x + (long long)n * V * ldx;
+  bf16* on = out + (long long)n * V * ldo;
+  const float* pn = psi_raw + (long long)n * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i / C8;
+    const int c0 = (int)(i - vox * C8) * 8;
+    const float s = 1.f / (1.f + __expf(-fmaf(__ldg(pn + vox), a, b)));
+    float v[8];
+    unpack8(ldg16_stream(xn + vox * ldx + c0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= s * sca[c0 + j];
+    stg16(on + vox * ldo + c0, pack8(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward 1: dx_direct = dout*s*ca ; dψn[v] = (Σ_c dout*x*ca) * s(1−s) ; dca[n][c] += Σ_v dout*x*s ;
+//             st_dpsi[n] += (Σ dψn, Σ dψn*x̂ψ)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
+    const bf16* __restrict__ dout, long long lddo, const bf16* __restrict__ x, long long ldx,
+    const float* __restrict__ psi_raw, const double* __restrict__ st_psi, const float* __restrict__ gpsi,
+    const float* __restrict__ bpsi_n, const float* __restrict__ ca, bf16* __restrict__ dx, long long lddx,
+    float* __restrict__ dpsin, double* __restrict__ dca, double* __restrict__ st_dpsi, long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* sca = sm; float* sdca = sm + C;
+  __shared__ float s_red[2];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { sca[c] = ca[(long long)n * C + c]; sdca[c] = 0.f; }
+  if (threadIdx.x < 2) s_red[threadIdx.x] = 0.f;
+  float mu, rstd;
+  mean_rstd_from(st_psi + (long long)n * 2, (double)V, eps, mu, rstd);
+  const float a = gpsi[0] * rstd, b = bpsi_n[0] - mu * a;
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int lanes_c = C8 < 32 ? C8 : 32;
+  const int vpw = 32 / lanes_c;
+  const int lane = threadIdx.x & 31;
+  const int lc = lane % lanes_c, lv = lane / lanes_c;
+  const int nchunks = (C8 + lanes_c - 1) / lanes_c;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bf16* don = dout + (long long)n * V * lddo;
+  const bf16* xn = x + (long long)n * V * ldx;
+  bf16* dxn = dx + (long long)n * V * lddx;
+  float acc_ca[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc_ca[j] = 0.f;
+  float r1 = 0.f, r2 = 0.f;
+  for (long long v0 = warp_id * vpw; v0 < V; v0 += nwarps * vpw) {
+    const long long v = v0 + lv;
+    float ds = 0.f, s = 0.f, xh = 0.f;
+    if (v < V) {
+      const float pr = __ldg(psi_raw + (long long)n * V + v);
+      s = 1.f / (1.f + __expf(-fmaf(pr, a, b)));
+      xh = (pr - mu) * rstd;
+      for (int c8 = lc; c8 < C8; c8 += lanes_c) {
+        float d[8], xv[8], o[8];
+        unpack8(ldg16_stream(don + v * lddo + c8 * 8), d);
+        unpack8(ldg16_stream(xn + v * ldx + c8 * 8), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float cc = sca[c8 * 8 + j];
+          const float dxv = d[j] * xv[j];
+          ds = fmaf(dxv, cc, ds);
+          o[j] = d[j] * s * cc;
+          if (nchunks == 1) acc_ca[j] = fmaf(dxv, s, acc_ca[j]);
+          else atomicAdd(&sdca[c8 * 8 + j], dxv * s);
+        }
+        stg16(dxn + v * lddx + c8 * 8, pack8(o));
+      }
+    }
+    for (int o = lanes_c >> 1; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    if (lc == 0 && v < V) {
+      const float dpn = ds * s * (1.f - s);
+      dpsin[(long long)n * V + v] = dpn;
+      r1 += dpn; r2 += dpn * xh;
+    }
+  }
+  if (nchunks == 1 && lc < C8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sdca[lc * 8 + j], acc_ca[j]);
+  }
+  r1 = warp_sum(r1); r2 = warp_sum(r2);
+  if (lane == 0) { atomicAdd(&s_red[0], r1); atomicAdd(&s_red[1], r2); }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dca[(long long)n * C + c], (double)sdca[c]);
+  if (threadIdx.x < 2) atomicAdd(&st_dpsi[(long long)n * 2 + threadIdx.x], (double)s_red[threadIdx.x]);
+}
+
+// SE backward (one block per sample).  Param grads are accumulated with fp32 atomics into caller-zeroed buffers.
+// xadd[n][c] = d(mean_c)/V : the constant the SE branch adds to every voxel of dx.
+__global__ void gate_se_bwd_kernel(const double* __restrict__ dca, const float* __restrict__ ca, const float* __restrict__ zbuf,
+                                   const float* __restrict__ meanbuf, const float* __restrict__ w1, const float* __restrict__ w2,
+                                   long long V, float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                   float* __restrict__ db2, float* __restrict__ xadd, int C) {
+  extern __shared__ float sm[];
+  const int R = C / 8;
+  float* dp2 = sm; float* dp1 = sm + C; float* z = sm + C + R; float* mean = sm + C + 2 * R;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float cc = ca[(long long)n * C + c];
+    dp2[c] = (float)dca[(long long)n * C + c] * cc * (1.f - cc);
+    mean[c] = meanbuf[(long long)n * C + c];
+    atomicAdd(&db2[c], dp2[c]);
+  }
+  for (int j = threadIdx.x; j < R; j += blockDim.x) z[j] = zbuf[(long long)n * R + j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * R; i += blockDim.x) {
+    const int c = i / R, j = i - c * R;
+    atomicAdd(&dW2[i], dp2[c] * z[j]);
+  }
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w2[(long long)c * R + j], dp2[c], a);
+    dp1[j] = z[j] > 0.f ? a : 0.f;
+    atomicAdd(&db1[j], dp1[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+    const int j = i / C, c = i - j * C;
+    atomicAdd(&dW1[i], dp1[j] * mean[c]);
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < R; ++j) a = fmaf(w1[(long long)j * C + c], dp1[j], a);
+    xadd[(long long)n * C + c] = a / (float)V;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward 2: dψr = GN1-backward(dψn) ; dz[c] = dψr * wψ[c] * [q_c>0]  (bf16 [N][V][F]) ;
+//   sums_g[n][c] += (Σdz, Σdz*x̂g) ; sums_x[n][c] += (Σdz, Σdz*x̂x) ; dwψ[c] += Σ dψr*q_c ; dbψ += Σ dψr
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
+    const float* __restrict__ dpsin, const float* __restrict__ psi_raw, const double* __restrict__ st_psi,
+    const double* __restrict__ st_dpsi, const float* __restrict__ gpsi, const bf16* __restrict__ g1r,
+    const bf16* __restrict__ x1r, const double* __restrict__ st_g, const double* __restrict__ st_x,
+    const float* __restrict__ gam_g, const float* __restrict__ bet_g, const float* __restrict__ gam_x,
+    const float* __restrict__ bet_x, const float* __restrict__ wpsi, bf16* __restrict__ dz, double* __restrict__ sums_g,
+    double* __restrict__ sums_x, float* __restrict__ dwpsi, float* __restrict__ dbpsi, long long V, int F, float eps) {
+  extern __shared__ float sm[];
+  float* mg = sm; float* rg = sm + F; float* mx = sm + 2 * F; float* rx = sm + 3 * F;
+  float* gg = sm + 4 * F; float* gx = sm + 5 * F; float* sh = sm + 6 * F; float* wp = sm + 7 * F;
+  float* red = sm + 8 * F;  // [4][F]: Σdz, Σdz*x̂g, Σdz*x̂x, Σdψr*q
+  __shared__ float s_db;
+  const int n = blockIdx.y;
+  const int cpg = F / 4;
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    float m1, r1, m2, r2;
+    mean_rstd_from(st_g + ((long long)n * 4 + c / cpg) * 2, (double)cpg * V, eps, m1, r1);
+    mean_rstd_from(st_x + ((long long)n * 4 + c / cpg) * 2, (double)cpg * V, eps, m2, r2);
+    mg[c] = m1; rg[c] = r1; mx[c] = m2; rx[c] = r2; gg[c] = gam_g[c]; gx[c] = gam_x[c];
+    sh[c] = bet_g[c] + bet_x[c]; wp[c] = wpsi[c];
+    red[c] = 0.f; red[F + c] = 0.f; red[2 * F + c] = 0.f; red[3 * F + c] = 0.f;
+  }
+  if (threadIdx.x == 0) s_db = 0.f;
+  float mu, rstd;
+  mean_rstd_from(st_psi + (long long)n * 2, (double)V, eps, mu, rstd);
+  const float gp = gpsi[0];
+  const float m1p = gp * (float)(st_dpsi[(long long)n * 2] / (double)V);
+  const float m2p = gp * (float)(st_dpsi[(long long)n * 2 + 1] / (double)V);
+  __syncthreads();
+  const int F8 = F >> 3;
+  const int lanes_c = F8 < 32 ? F8 : 32;
+  const int vpw = 32 / lanes_c;
+  const int lane = threadIdx.x & 31;
+  const int lc = lane % lanes_c, lv = lane / lanes_c;
+  const int nchunks = (F8 + lanes_c - 1) / lanes_c;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bf16* gn_ = g1r + (long long)n * V * F;
+  const bf16* xn_ = x1r + (long long)n * V * F;
+  bf16* dzn = dz + (long long)n * V * F;
+  float a0[8], a1[8], a2[8], a3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; }
+  float db = 0.f;
+  for (long long v0 = warp_id * vpw; v0 < V; v0 += nwarps * vpw) {
+    const long long v = v0 + lv;
+    if (v >= V) continue;
+    const float pr = __ldg(psi_raw + (long long)n * V + v);
+    const float xh = (pr - mu) * rstd;
+    const float dpr = rstd * (gp * __ldg(dpsin + (long long)n * V + v) - m1p - xh * m2p);
+    if (lc == 0) db += dpr;
+    for (int c8 = lc; c8 < F8; c8 += lanes_c) {
+      float a[8], b[8], o[8];
+      unpack8(ldg16_stream(gn_ + v * F + c8 * 8), a);
+      unpack8(ldg16_stream(xn_ + v * F + c8 * 8), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c8 * 8 + j;
+        const float xg = (a[j] - mg[c]) * rg[c], xx = (b[j] - mx[c]) * rx[c];
+        const float q = fmaf(xg, gg[c], fmaf(xx, gx[c], sh[c]));
+        const float dzv = q > 0.f ? dpr * wp[c] : 0.f;
+        o[j] = dzv;
+        const float qq = fmaxf(q, 0.f);
+        if (nchunks == 1) {
+          a0[j] += dzv; a1[j] = fmaf(dzv, xg, a1[j]); a2[j] = fmaf(dzv, xx, a2[j]); a3[j] = fmaf(dpr, qq, a3[j]);
+        } else {
+          atomicAdd(&red[c], dzv); atomicAdd(&red[F + c], dzv * xg); atomicAdd(&red[2 * F + c], dzv * xx);
+          atomicAdd(&red[3 * F + c], dpr * qq);
+        }
+      }
+      stg16(dzn + v * F + c8 * 8, pack8(o));
+    }
+  }
+  if (nchunks == 1 && lc < F8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[lc * 8 + j], a0[j]); atomicAdd(&red[F + lc * 8 + j], a1[j]);
+      atomicAdd(&red[2 * F + lc * 8 + j], a2[j]); atomicAdd(&red[3 * F + lc * 8 + j], a3[j]);
+    }
+  }
+  db = warp_sum(db);
+  if (lane == 0) atomicAdd(&s_db, db);
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += blockDim.x) {
+    atomicAdd(&sums_g[((long long)n * F + c) * 2], (double)red[c]);
+    atomicAdd(&sums_g[((long long)n * F + c) * 2 + 1], (double)red[F + c]);
+    atomicAdd(&sums_x[((long long)n * F + c) * 2], (double)red[c]);
+    atomicAdd(&sums_x[((long long)n * F + c) * 2 + 1], (double)red[2 * F + c]);
+    atomicAdd(&dwpsi[c], red[3 * F + c]);
+  }
+  if (threadIdx.x == 0) atomicAdd(dbpsi, s_db);
+}
+
+// dγψ = Σ_n Σ_v dψn*x̂ψ ; dβψ = Σ_n Σ_v dψn
+__global__ void gate_psi_norm_grad_kernel(const double* __restrict__ st_dpsi, int N, float* dgpsi, float* dbpsi_n) {
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int n = 0; n < N; ++n) { b += st_dpsi[2 * n]; a += st_dpsi[2 * n + 1]; }
+    dgpsi[0] = (float)a; dbpsi_n[0] = (float)b;
+  }
+}
+
+// dx[n][v][c] += xadd[n][c]   (SE-branch contribution, constant per channel)
+__global__ void __launch_bounds__(256) add_channel_const_kernel(bf16* __restrict__ dx, long long lddx, const float* __restrict__ xadd,
+                                                                long long V, int C) {
+  extern __shared__ float sa[];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sa[c] = xadd[(long long)n * C + c];
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = V * C8;
+  bf16* dxn = dx + (long long)n * V * lddx;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i / C8;
+    const int c0 = (int)(i - vox * C8) * 8;
+    float v[8];
+    unpack8(ldg16(dxn + vox * lddx + c0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += sa[c0 + j];
+    stg16(dxn + vox * lddx + c0, pack8(v));
+  }
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+extern "C" {
+
+int b3d_gate_psi_fwd(const void* g1r, const void* x1r, const double* st_g, const double* st_x, const float* gam_g,
+                     const float* bet_g, const float* gam_x, const float* bet_x, const float* wpsi, const float* bpsi,
+                     float* psi_raw, double* st_psi, int N, long long V, int F, float eps, void* stream) {
+  B3D_REQUIRE(F % 8 == 0 && F % 4 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_fwd: F=%d unsupported", F);
+  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
+  gate_psi_fwd_kernel<<<grid, 256, 4 * F * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi, 0.f, bpsi, psi_raw, st_psi, V, F, eps);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gate_se_fwd(const double* xsum, long long V, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* ca, float* zbuf, float* meanbuf, int N, int C, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C <= 4096, "gate_se_fwd: bad C");
+  gate_se_fwd_kernel<<<N, 256, (C + C / 8) * sizeof(float), (cudaStream_t)stream>>>(xsum, V, w1, b1, w2, b2, ca, zbuf, meanbuf, C);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gate_apply_fwd(const void* x, long long ldx, const float* psi_raw, const double* st_psi, const float* gpsi,
+                       const float* bpsi_n, const float* ca, void* out, long long ldo, int N, long long V, int C,
+                       float eps, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C <= 4096, "gate_apply_fwd: bad C");
+  dim3 grid(gt_blocks_per_sample(V * (C / 8), 512, N), N);
+  gate_apply_fwd_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n,
+                                                                               ca, (bf16*)out, ldo, V, C, eps);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long long ldx, const float* psi_raw,
+                       const double* st_psi, const float* gpsi, const float* bpsi_n, const float* ca, void* dx,
+                       long long lddx, float* dpsin, double* dca, double* st_dpsi, int N, long long V, int C, float eps,
+                       void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && (pow2(C / 8) || (C / 8) % 32 == 0) && C <= 4096, "gate_apply_bwd: C=%d unsupported", C);
+  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
+  gate_apply_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)dout, lddo, (const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n, ca, (bf16*)dx, lddx, dpsin, dca, st_dpsi, V, C, eps);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gate_se_bwd(const double* dca, const float* ca, const float* zbuf, const float* meanbuf, const float* w1,
+                    const float* w2, long long V, float* dW1, float* db1, float* dW2, float* db2, float* xadd, int N, int C,
+                    void* stream) {
+  gate_se_bwd_kernel<<<N, 256, (2 * C + 2 * (C / 8)) * sizeof(float), (cudaStream_t)stream>>>(dca, ca, zbuf, meanbuf, w1, w2, V, dW1,
+                                                                                             db1, dW2, db2, xadd, C);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_psi, const double* st_dpsi,
+                     const float* gpsi, const void* g1r, const void* x1r, const double* st_g, const double* st_x,
+                     const float* gam_g, const float* bet_g, const float* gam_x, const float* bet_x, const float* wpsi,
+                     void* dz, double* sums_g, double* sums_x, float* dwpsi, float* dbpsi, float* dgpsi, float* dbpsi_n,
+                     int N, long long V, int F, float eps, void* stream) {
+  B3D_REQUIRE(F % 8 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_bwd: F=%d unsupported", F);
+  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
+  gate_psi_bwd_kernel<<<grid, 256, 12 * F * sizeof(float), (cudaStream_t)stream>>>(
+      dpsin, psi_raw, st_psi, st_dpsi, gpsi, (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi,
+      (bf16*)dz, sums_g, sums_x, dwpsi, dbpsi, V, F, eps);
+  gate_psi_norm_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st_dpsi, N, dgpsi, dbpsi_n);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_add_channel_const(void* dx, long long lddx, const float* xadd, int N, long long V, int C, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C <= 4096, "add_channel_const: bad C");
+  dim3 grid(gt_blocks_per_sample(V * (C / 8), 512, N), N);
+  add_channel_const_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((bf16*)dx, lddx, xadd, V, C);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+}  // extern "C"

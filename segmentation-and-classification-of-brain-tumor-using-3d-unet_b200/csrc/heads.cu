@@ -1,0 +1,488 @@
+// heads.cu — the 4-class output heads of the U-Net (all HBM-bound, CUDA cores):
+//   * deep-supervision head: Conv1x1(f_i -> K)+bias on an encoder skip, then F.interpolate(trilinear,
+//     align_corners=False) to full resolution                      /root/reference/main.py:137-140,164-171
+//   * final head: BatchNorm3d(F2) (batch stats in train, running stats in eval, momentum 0.1) -> ReLU -> Conv1x1(F2 -> K)
+//     applied to the output of final_conv.0                         /root/reference/main.py:129-134,198
+// Logits are produced as fp32 NCDHW (what the reference returns and what the loss reads).  K (classes) is fixed to 4
+// (BraTS labels 0..3, main.py:336 / train_model.py:174); other values are rejected loudly.
+#include "b3d_common.cuh"
+#include "b3d_internal.h"
+#include <algorithm>
+
+#define KCLS 4
+
+static int hd_blocks(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)b3d_num_sms() * 16;
+  return (int)std::max<long long>(1, std::min(b, cap));
+}
+
+// ------------------------------------------------------------------------------------------------
+// deep-supervision 1x1 head: l[n][v][k] = b[k] + Σ_c skip[n][v][c] * W[k][c]      (fp32 float4 per voxel)
+// lanes of a warp = (voxel sub-index, 8-channel chunk); partial dots are reduced with shuffles.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ds_head_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float4* __restrict__ out,
+                                                          long long NV, int C) {
+  extern __shared__ float sw[];  // [K][C]
+  for (int i = threadIdx.x; i < KCLS * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int lanes_c = C8 < 32 ? C8 : 32;       // lanes cooperating on one voxel
+  const int vpw = 32 / lanes_c;                // voxels per warp iteration
+  const int lane = threadIdx.x & 31;
+  const int lc = lane % lanes_c, lv = lane / lanes_c;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long v0 = warp_id * vpw; v0 < NV; v0 += nwarps * vpw) {
+    const long long v = v0 + lv;
+    float acc[KCLS] = {0.f, 0.f, 0.f, 0.f};
+    if (v < NV) {
+      for (int c8 = lc; c8 < C8; c8 += lanes_c) {
+        float a[8];
+        unpack8(ldg16_stream(x + v * ldx + c8 * 8), a);
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(a[j], sw[k * C + c8 * 8 + j], acc[k]);
+      }
+    }
+    for (int o = lanes_c >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < KCLS; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lc == 0 && v < NV) out[v] = make_float4(acc[0] + b[0], acc[1] + b[1], acc[2] + b[2], acc[3] + b[3]);
+  }
+}
+
+// backward of the 1x1 head: dl is PLANAR fp32 [N][K][Vs]; dskip[n][v][c] (+)= Σ_k dl_k W[k][c];
+// dW[k][c] += Σ dl_k skip_c ; db[k] += Σ dl_k   (fp32 atomics into caller-zeroed buffers)
+template <bool ACC>
+__global__ void __launch_bounds__(256) ds_head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x,
+                                                          long long ldx, const float* __restrict__ w, bf16* __restrict__ dx,
+                                                          long long lddx, float* __restrict__ dW, float* __restrict__ db,
+                                                          int N, long long Vs, int C) {
+  extern __shared__ float sw[];  // [K][C] weights, then [K][C] dW accum, then [K] db accum
+  float* sdw = sw + KCLS * C;
+  float* sdb = sdw + KCLS * C;
+  for (int i = threadIdx.x; i < KCLS * C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+  if (threadIdx.x < KCLS) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int lanes_c = C8 < 32 ? C8 : 32;
+  const int vpw = 32 / lanes_c;
+  const int lane = threadIdx.x & 31;
+  const int lc = lane % lanes_c, lv = lane / lanes_c;
+  const long long NV = (long long)N * Vs;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nchunks = (C8 + lanes_c - 1) / lanes_c;  // chunks per lane (1 unless C > 256)
+  float gw[KCLS][8];
+#pragma unroll
+  for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gw[k][j] = 0.f;
+  float gb[KCLS] = {0.f, 0.f, 0.f, 0.f};
+  for (long long v0 = warp_id * vpw; v0 < NV; v0 += nwarps * vpw) {
+    const long long v = v0 + lv;
+    if (v >= NV) continue;
+    const long long n = v / Vs, vs = v - n * Vs;
+    float g[KCLS];
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k) g[k] = __ldg(dl + (n * KCLS + k) * Vs + vs);
+    if (lc == 0) {
+#pragma unroll
+      for (int k = 0; k < KCLS; ++k) gb[k] += g[k];
+    }
+    for (int c8 = lc; c8 < C8; c8 += lanes_c) {
+      float a[8], o[8];
+      unpack8(ldg16_stream(x + v * ldx + c8 * 8), a);
+      if (ACC) unpack8(ldg16(dx + v * lddx + c8 * 8), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k) s = fmaf(g[k], sw[k * C + c8 * 8 + j], s);
+        o[j] = ACC ? o[j] + s : s;
+      }
+      stg16(dx + v * lddx + c8 * 8, pack8(o));
+      if (nchunks == 1) {
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gw[k][j] = fmaf(g[k], a[j], gw[k][j]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(&sdw[k * C + c8 * 8 + j], g[k] * a[j]);
+      }
+    }
+  }
+  if (nchunks == 1 && lc < C8) {
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sdw[k * C + lc * 8 + j], gw[k][j]);
+  }
+  if (lc == 0) {
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k) atomicAdd(&sdb[k], gb[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KCLS * C; i += blockDim.x) atomicAdd(&dW[i], sdw[i]);
+  if (threadIdx.x < KCLS) atomicAdd(&db[threadIdx.x], sdb[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// trilinear upsample (align_corners=False) of low-res logits float4[N][Dl][Hl][Wl] to planar fp32 [N][K][D][H][W]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lerp_src(int o, float scale, int nin, int& i0, int& i1, float& l1) {
+  float src = scale * (o + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > nin - 1) i0 = nin - 1;
+  i1 = i0 + ((i0 < nin - 1) ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) trilinear_up_fwd_kernel(const float4* __restrict__ lo, float* __restrict__ out, int N,
+                                                               int Dl, int Hl, int Wl, int D, int H, int W) {
+  const long long V = (long long)D * H * W;
+  const long long total = (long long)N * V;
+  const float sd = (float)Dl / D, shh = (float)Hl / H, sww = (float)Wl / W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H); t /= H;
+    const int z = (int)(t % D); const int n = (int)(t / D);
+    int z0, z1, y0, y1, x0, x1; float lz, ly, lx;
+    lerp_src(z, sd, Dl, z0, z1, lz); lerp_src(y, shh, Hl, y0, y1, ly); lerp_src(x, sww, Wl, x0, x1, lx);
+    const float4* b = lo + (long long)n * Dl * Hl * Wl;
+#define AT(zz, yy, xx) __ldg(b + ((long long)(zz) * Hl + (yy)) * Wl + (xx))
+    const float4 v000 = AT(z0, y0, x0), v001 = AT(z0, y0, x1), v010 = AT(z0, y1, x0), v011 = AT(z0, y1, x1);
+    const float4 v100 = AT(z1, y0, x0), v101 = AT(z1, y0, x1), v110 = AT(z1, y1, x0), v111 = AT(z1, y1, x1);
+#undef AT
+    const float wz0 = 1.f - lz, wy0 = 1.f - ly, wx0 = 1.f - lx;
+#define MIX(f)                                                                                         \
+  (wz0 * (wy0 * (wx0 * v000.f + lx * v001.f) + ly * (wx0 * v010.f + lx * v011.f)) +                    \
+   lz * (wy0 * (wx0 * v100.f + lx * v101.f) + ly * (wx0 * v110.f + lx * v111.f)))
+    const long long vv = ((long long)z * H + y) * W + x;
+    float* o = out + (long long)n * KCLS * V + vv;
+    o[0] = MIX(x); o[V] = MIX(y); o[2 * V] = MIX(z); o[3 * V] = MIX(w);
+#undef MIX
+  }
+}
+
+// adjoint of 1-D linear upsampling along one axis of a planar fp32 tensor [outer][Lout][inner] -> [outer][Lin][inner]
+__global__ void __launch_bounds__(256) lerp_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, long long outer,
+                                                           int Lout, int Lin, long long inner) {
+  const long long total = outer * Lin * inner;
+  const float scale = (float)Lin / Lout;
+  const int s = Lout / Lin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const long long q = t % inner; t /= inner;
+    const int li = (int)(t % Lin); const long long ou = t / Lin;
+    const float* src = in + ou * Lout * inner + q;
+    float acc = 0.f;
+    const int o_lo = max(0, s * (li - 1)), o_hi = min(Lout, s * (li + 2));
+    for (int o = o_lo; o < o_hi; ++o) {
+      int i0, i1; float l1;
+      lerp_src(o, scale, Lin, i0, i1, l1);
+      float wgt = 0.f;
+      if (i0 == li) wgt += 1.f - l1;
+      if (i1 == li) wgt += l1;
+      if (wgt != 0.f) acc = fmaf(wgt, __ldg(src + (long long)o * inner), acc);
+    }
+    out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// final head:  logits[n][k][v] = b2[k] + Σ_c W2[k][c] * relu(BN(h[n][v][c]))
+// bn: [0..F2) = mean, [F2..2F2) = rstd  (computed by final_bn_prepare from batch or running statistics)
+// ------------------------------------------------------------------------------------------------
+__global__ void final_bn_prepare_kernel(const double* __restrict__ stats, double count, int train, float* running_mean,
+                                        float* running_var, long long* num_batches, float momentum, float eps,
+                                        float* __restrict__ bn, int F2, int update_running) {
+  const int c = threadIdx.x;
+  if (c >= F2) return;
+  float mean, var;
+  if (train) {
+    const double mu = stats[2 * c] / count;
+    double v = stats[2 * c + 1] / count - mu * mu;
+    if (v < 0) v = 0;
+    mean = (float)mu; var = (float)v;
+    if (update_running) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(v * count / (count - 1.0));
+      if (c == 0 && num_batches) *num_batches += 1;
+    }
+  } else {
+    mean = running_mean[c]; var = running_var[c];
+  }
+  bn[c] = mean;
+  bn[F2 + c] = rsqrtf(var + eps);
+}
+
+template <int F2>
+__global__ void __launch_bounds__(256) final_head_fwd_kernel(const bf16* __restrict__ h, long long ldh, const float* __restrict__ bn,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ w2, const float* __restrict__ b2,
+                                                             float* __restrict__ out, int N, long long V) {
+  __shared__ float s_sc[F2], s_sh[F2], s_w[KCLS * F2], s_b[KCLS];
+  if (threadIdx.x < F2) {
+    const float sc = gamma[threadIdx.x] * bn[F2 + threadIdx.x];
+    s_sc[threadIdx.x] = sc; s_sh[threadIdx.x] = beta[threadIdx.x] - bn[threadIdx.x] * sc;
+  }
+  for (int i = threadIdx.x; i < KCLS * F2; i += blockDim.x) s_w[i] = w2[i];
+  if (threadIdx.x < KCLS) s_b[threadIdx.x] = b2[threadIdx.x];
+  __syncthreads();
+  const long long total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / V, v = i - n * V;
+    float acc[KCLS];
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k) acc[k] = s_b[k];
+#pragma unroll
+    for (int c8 = 0; c8 < F2 / 8; ++c8) {
+      float a[8];
+      unpack8(ldg16_stream(h + i * ldh + c8 * 8), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float r = fmaxf(fmaf(a[j], s_sc[c8 * 8 + j], s_sh[c8 * 8 + j]), 0.f);
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k) acc[k] = fmaf(r, s_w[k * F2 + c8 * 8 + j], acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k) out[(n * KCLS + k) * V + v] = acc[k];
+  }
+}
+
+// backward phase 1: red[0..F2) Σdz, [F2..2F2) Σdz*xhat, then dW2 [K][F2], then db2 [K]   (double atomics, caller zeroes)
+template <int F2>
+__global__ void __launch_bounds__(256) final_head_bwd_reduce_kernel(const float* __restrict__ dl, const bf16* __restrict__ h,
+                                                                    long long ldh, const float* __restrict__ bn,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    const float* __restrict__ w2, double* __restrict__ red, int N,
+                                                                    long long V) {
+  constexpr int NR = 2 * F2 + KCLS * F2 + KCLS;
+  __shared__ float s_mean[F2], s_rstd[F2], s_g[F2], s_bt[F2], s_w[KCLS * F2];
+  __shared__ float s_red[NR];
+  if (threadIdx.x < F2) {
+    s_mean[threadIdx.x] = bn[threadIdx.x]; s_rstd[threadIdx.x] = bn[F2 + threadIdx.x];
+    s_g[threadIdx.x] = gamma[threadIdx.x]; s_bt[threadIdx.x] = beta[threadIdx.x];
+  }
+  for (int i = threadIdx.x; i < KCLS * F2; i += blockDim.x) s_w[i] = w2[i];
+  for (int i = threadIdx.x; i < NR; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  float a_dz[F2], a_dzx[F2], a_w[KCLS][F2], a_b[KCLS];
+#pragma unroll
+  for (int c = 0; c < F2; ++c) { a_dz[c] = 0.f; a_dzx[c] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < KCLS; ++k) {
+    a_b[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < F2; ++c) a_w[k][c] = 0.f;
+  }
+  const long long total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / V, v = i - n * V;
+    float g[KCLS];
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k) { g[k] = __ldg(dl + (n * KCLS + k) * V + v); a_b[k] += g[k]; }
+#pragma unroll
+    for (int c8 = 0; c8 < F2 / 8; ++c8) {
+      float a[8];
+      unpack8(ldg16_stream(h + i * ldh + c8 * 8), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c8 * 8 + j;
+        const float xh = (a[j] - s_mean[c]) * s_rstd[c];
+        const float hn = fmaf(xh, s_g[c], s_bt[c]);
+        const float r = fmaxf(hn, 0.f);
+        float dr = 0.f;
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k) { dr = fmaf(g[k], s_w[k * F2 + c], dr); a_w[k][c] = fmaf(g[k], r, a_w[k][c]); }
+        const float dz = hn > 0.f ? dr : 0.f;
+        a_dz[c] += dz; a_dzx[c] += dz * xh;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < F2; ++c) {
+    const float s1 = warp_sum(a_dz[c]), s2 = warp_sum(a_dzx[c]);
+    if (lane == 0) { atomicAdd(&s_red[c], s1); atomicAdd(&s_red[F2 + c], s2); }
+  }
+#pragma unroll
+  for (int k = 0; k < KCLS; ++k) {
+#pragma unroll
+    for (int c = 0; c < F2; ++c) {
+      const float s = warp_sum(a_w[k][c]);
+      if (lane == 0) atomicAdd(&s_red[2 * F2 + k * F2 + c], s);
+    }
+    const float sb = warp_sum(a_b[k]);
+    if (lane == 0) atomicAdd(&s_red[2 * F2 + KCLS * F2 + k], sb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NR; i += blockDim.x) atomicAdd(&red[i], (double)s_red[i]);
+}
+
+// backward phase 2: dh = BN-backward(dz) as bf16 [N][V][F2]; train uses batch statistics, eval the running ones
+template <int F2>
+__global__ void __launch_bounds__(256) final_head_bwd_apply_kernel(const float* __restrict__ dl, const bf16* __restrict__ h,
+                                                                   long long ldh, const float* __restrict__ bn,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   const float* __restrict__ w2, const double* __restrict__ red,
+                                                                   int train, bf16* __restrict__ dh, long long lddh, int N,
+                                                                   long long V) {
+  __shared__ float s_mean[F2], s_rstd[F2], s_g[F2], s_bt[F2], s_w[KCLS * F2], s_m1[F2], s_m2[F2];
+  const double cnt = (double)N * (double)V;
+  if (threadIdx.x < F2) {
+    const int c = threadIdx.x;
+    s_mean[c] = bn[c]; s_rstd[c] = bn[F2 + c]; s_g[c] = gamma[c]; s_bt[c] = beta[c];
+    s_m1[c] = train ? (float)(red[c] / cnt) : 0.f;
+    s_m2[c] = train ? (float)(red[F2 + c] / cnt) : 0.f;
+  }
+  for (int i = threadIdx.x; i < KCLS * F2; i += blockDim.x) s_w[i] = w2[i];
+  __syncthreads();
+  const long long total = (long long)N * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / V, v = i - n * V;
+    float g[KCLS];
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k) g[k] = __ldg(dl + (n * KCLS + k) * V + v);
+#pragma unroll
+    for (int c8 = 0; c8 < F2 / 8; ++c8) {
+      float a[8], o[8];
+      unpack8(ldg16_stream(h + i * ldh + c8 * 8), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c8 * 8 + j;
+        const float xh = (a[j] - s_mean[c]) * s_rstd[c];
+        const float hn = fmaf(xh, s_g[c], s_bt[c]);
+        float dr = 0.f;
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k) dr = fmaf(g[k], s_w[k * F2 + c], dr);
+        const float dz = hn > 0.f ? dr : 0.f;
+        o[j] = s_g[c] * s_rstd[c] * (dz - s_m1[c] - xh * s_m2[c]);
+      }
+      stg16(dh + i * lddh + c8 * 8, pack8(o));
+    }
+  }
+}
+
+// unpack the reduction buffer into parameter gradients (fp32)
+__global__ void final_head_param_grad_kernel(const double* __restrict__ red, int F2, float* dgamma, float* dbeta, float* dW2,
+                                             float* db2) {
+  const int i = threadIdx.x;
+  if (i < F2) { dbeta[i] = (float)red[i]; dgamma[i] = (float)red[F2 + i]; }
+  for (int j = i; j < KCLS * F2; j += blockDim.x) dW2[j] = (float)red[2 * F2 + j];
+  if (i < KCLS) db2[i] = (float)red[2 * F2 + KCLS * F2 + i];
+}
+
+extern "C" {
+
+int b3d_ds_head_fwd(const void* x, long long ldx, const float* w, const float* b, float* out, long long NV, int C, int K,
+                    void* stream) {
+  B3D_REQUIRE(K == KCLS, "ds_head: only %d output classes supported (got %d)", KCLS, K);
+  B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
+  ds_head_fwd_kernel<<<hd_blocks(NV * 8, 256), 256, KCLS * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, w, b, (float4*)out, NV, C);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
+                    int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream) {
+  B3D_REQUIRE(K == KCLS, "ds_head: only %d output classes supported (got %d)", KCLS, K);
+  B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
+  const size_t smem = (2 * KCLS * C + KCLS) * sizeof(float);
+  const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 4);
+  if (accumulate)
+    ds_head_bwd_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C);
+  else
+    ds_head_bwd_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_trilinear_up_fwd(const float* lo, float* out, int N, int Dl, int Hl, int Wl, int D, int H, int W, int K,
+                         void* stream) {
+  B3D_REQUIRE(K == KCLS, "trilinear_up: only %d classes supported", KCLS);
+  trilinear_up_fwd_kernel<<<hd_blocks((long long)N * D * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)lo, out, N, Dl, Hl, Wl, D, H, W);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// dup planar [N][K][D][H][W] -> dlo planar [N][K][Dl][Hl][Wl]; tmp must hold N*K*D*H*Wl + N*K*D*Hl*Wl floats
+int b3d_trilinear_up_bwd(const float* dup, float* dlo, float* tmp, int N, int Dl, int Hl, int Wl, int D, int H, int W,
+                         int K, void* stream) {
+  B3D_REQUIRE(D % Dl == 0 && H % Hl == 0 && W % Wl == 0, "trilinear_up_bwd: integer scale factors only");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long NK = (long long)N * K;
+  float* t1 = tmp;
+  float* t2 = tmp + NK * D * H * Wl;
+  long long tot = NK * D * H * Wl;
+  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(dup, t1, NK * D * H, W, Wl, 1);
+  tot = NK * D * Hl * Wl;
+  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(t1, t2, NK * D, H, Hl, Wl);
+  tot = NK * Dl * Hl * Wl;
+  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(t2, dlo, NK, D, Dl, (long long)Hl * Wl);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_final_bn_prepare(const double* stats, double count, int train, float* running_mean, float* running_var,
+                         long long* num_batches, float momentum, float eps, float* bn, int F2, int update_running,
+                         void* stream) {
+  B3D_REQUIRE(F2 <= 64, "final_bn_prepare: F2 too large");
+  final_bn_prepare_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(stats, count, train, running_mean, running_var, num_batches,
+                                                             momentum, eps, bn, F2, update_running);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+#define F2_DISPATCH(F2v, CALL8, CALL16, CALL32)                                        \
+  if (F2v == 8) { CALL8; } else if (F2v == 16) { CALL16; } else if (F2v == 32) { CALL32; } \
+  else { b3d_set_error("final head: F2=%d unsupported (8,16,32)", F2v); return B3D_ERR_UNSUPPORTED; }
+
+int b3d_final_head_fwd(const void* h, long long ldh, const float* bn, const float* gamma, const float* beta,
+                       const float* w2, const float* b2, float* out, int N, long long V, int F2, int K, void* stream) {
+  B3D_REQUIRE(K == KCLS, "final_head: only %d output classes supported (got %d)", KCLS, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = hd_blocks((long long)N * V, 256);
+  F2_DISPATCH(F2,
+    (final_head_fwd_kernel<8><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V)),
+    (final_head_fwd_kernel<16><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V)),
+    (final_head_fwd_kernel<32><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V)));
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// red: double [2*F2 + K*F2 + K], caller zeroes
+int b3d_final_head_bwd(const float* dl, const void* h, long long ldh, const float* bn, const float* gamma,
+                       const float* beta, const float* w2, double* red, int train, void* dh, long long lddh,
+                       float* dgamma, float* dbeta, float* dW2, float* db2, int N, long long V, int F2, int K,
+                       void* stream) {
+  B3D_REQUIRE(K == KCLS, "final_head: only %d output classes supported (got %d)", KCLS, K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rblocks = std::min(hd_blocks((long long)N * V, 256), b3d_num_sms() * 2);
+  const int blocks = hd_blocks((long long)N * V, 256);
+  F2_DISPATCH(F2,
+    (final_head_bwd_reduce_kernel<8><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V)),
+    (final_head_bwd_reduce_kernel<16><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V)),
+    (final_head_bwd_reduce_kernel<32><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V)));
+  F2_DISPATCH(F2,
+    (final_head_bwd_apply_kernel<8><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V)),
+    (final_head_bwd_apply_kernel<16><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V)),
+    (final_head_bwd_apply_kernel<32><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V)));
+  final_head_param_grad_kernel<<<1, 128, 0, st>>>(red, F2, dgamma, dbeta, dW2, db2);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+}  // extern "C"

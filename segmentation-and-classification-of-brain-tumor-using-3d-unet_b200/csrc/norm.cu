@@ -1,0 +1,294 @@
+// norm.cu — fused GroupNorm (+ReLU) (+GroupNorm'd residual add) forward and backward, NDHWC bf16, fp32/fp64 statistics.
+//
+// Reference semantics: nn.GroupNorm(G, C, eps=1e-5) + nn.ReLU in DoubleConv3D (/root/reference/main.py:215-233,235-242):
+//     a1  = relu(GN8(y1))                       -> b3d_gn_apply(relu=1)
+//     out = relu(GN8(y2)) + GN8'(r)             -> b3d_gn_apply(relu=1, residual r)     (no ReLU after the add)
+// The per-(sample, group) sum / sum-of-squares come from the producing convolution's epilogue (conv_igemm.cu), so the
+// forward is ONE read + ONE write of the tensor (HBM-bound: 2T resp. 3T bytes).
+// Backward:  dz = dy * [relu mask];  dx = rstd * (dz*γ − mean_g(dz*γ) − x̂ * mean_g(dz*γ*x̂))
+//   phase 1 (b3d_gn_bwd_reduce): per-(n,c) Σdz, Σdz·x̂        (one read of dy and y)
+//   phase 2 (b3d_gn_bwd_apply) : dx                           (one read of dy and y, one write)
+#include "b3d_common.cuh"
+#include "b3d_internal.h"
+#include <algorithm>
+
+#define GN_THREADS 256
+#define GN_MAXC 2048
+
+__device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, int n, int G, int g, double m, float eps,
+                                             float& mean, float& rstd) {
+  const double s = stats[((long long)n * G + g) * 2], q = stats[((long long)n * G + g) * 2 + 1];
+  const double mu = s / m;
+  double var = q / m - mu * mu;
+  if (var < 0) var = 0;
+  mean = (float)mu;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// out = act(GN(y)) [+ GN_r(r) | + r]
+template <bool RELU, int RES>  // RES: 0 none, 1 GroupNorm'd residual, 2 plain residual
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
+    const bf16* __restrict__ y, long long ldy, const double* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int G, const bf16* __restrict__ r, long long ldr, const double* __restrict__ stats_r,
+    const float* __restrict__ gamma_r, const float* __restrict__ beta_r, int Gr, bf16* __restrict__ out, long long ldo,
+    long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* sc = sm; float* sh = sm + C; float* scr = sm + 2 * C; float* shr = sm + 3 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd(stats, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    const float s = gamma[c] * rstd;
+    sc[c] = s; sh[c] = beta[c] - mean * s;
+    if (RES == 1) {
+      gn_mean_rstd(stats_r, n, Gr, c / (C / Gr), (double)(C / Gr) * (double)V, eps, mean, rstd);
+      const float s2 = gamma_r[c] * rstd;
+      scr[c] = s2; shr[c] = beta_r[c] - mean * s2;
+    }
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = V * C8;
+  const bf16* yn = y + (long long)n * V * ldy;
+  const bf16* rn = (RES != 0) ? r + (long long)n * V * ldr : nullptr;
+  bf16* on = out + (long long)n * V * ldo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i / C8;
+    const int c0 = (int)(i - vox * C8) * 8;
+    float a[8];
+    unpack8(ldg16_stream(yn + vox * ldy + c0), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(a[j], sc[c0 + j], sh[c0 + j]);
+      if (RELU) t = fmaxf(t, 0.f);
+      a[j] = t;
+    }
+    if (RES != 0) {
+      float b[8];
+      unpack8(ldg16_stream(rn + vox * ldr + c0), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += (RES == 1) ? fmaf(b[j], scr[c0 + j], shr[c0 + j]) : b[j];
+    }
+    stg16(on + vox * ldo + c0, pack8(a));
+  }
+}
+
+// phase 1: sums[n][c][0] += Σ_v dz ; sums[n][c][1] += Σ_v dz*xhat        (dz = dy * relu-mask)
+template <bool RELU>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y, long long ldy,
+    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
+    double* __restrict__ sums, long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* s_mean = sm; float* s_rstd = sm + C; float* s_g = sm + 2 * C; float* s_b = sm + 3 * C;
+  float* red = sm + 4 * C;  // [2][C] block accumulators
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd(stats, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    s_mean[c] = mean; s_rstd[c] = rstd; s_g[c] = gamma[c]; s_b[c] = beta[c];
+    red[c] = 0.f; red[C + c] = 0.f;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  // thread owns a fixed 8-channel chunk when blockDim % C8 == 0 (C8 <= 256 and power of two in practice); otherwise
+  // fall back to per-element shared atomics.
+  const bool fixed = (blockDim.x % C8) == 0;
+  const bf16* dyn = dy + (long long)n * V * lddy;
+  const bf16* yn = y + (long long)n * V * ldy;
+  const long long total = V * C8;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+  int myc0 = -1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i / C8;
+    const int c0 = (int)(i - vox * C8) * 8;
+    float d[8], x[8];
+    unpack8(ldg16_stream(dyn + vox * lddy + c0), d);
+    unpack8(ldg16_stream(yn + vox * ldy + c0), x);
+    if (fixed) {
+      myc0 = c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - s_mean[c0 + j]) * s_rstd[c0 + j];
+        float dz = d[j];
+        if (RELU && fmaf(xh, s_g[c0 + j], s_b[c0 + j]) <= 0.f) dz = 0.f;
+        a1[j] += dz; a2[j] += dz * xh;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - s_mean[c0 + j]) * s_rstd[c0 + j];
+        float dz = d[j];
+        if (RELU && fmaf(xh, s_g[c0 + j], s_b[c0 + j]) <= 0.f) dz = 0.f;
+        atomicAdd(&red[c0 + j], dz); atomicAdd(&red[C + c0 + j], dz * xh);
+      }
+    }
+  }
+  if (fixed && myc0 >= 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&red[myc0 + j], a1[j]); atomicAdd(&red[C + myc0 + j], a2[j]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&sums[((long long)n * C + c) * 2], (double)red[c]);
+    atomicAdd(&sums[((long long)n * C + c) * 2 + 1], (double)red[C + c]);
+  }
+}
+
+// phase 2: dx = A_c*dz − B_g − xhat*Cg ; optionally accumulates into dx (dx += ...)
+template <bool RELU, bool ACC>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y, long long ldy,
+    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
+    const double* __restrict__ sums, bf16* __restrict__ dx, long long lddx, long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* s_mean = sm; float* s_rstd = sm + C; float* s_g = sm + 2 * C; float* s_b = sm + 3 * C;
+  float* s_B = sm + 4 * C; float* s_C = sm + 5 * C;  // per channel copies of the group terms
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const double m = (double)cpg * (double)V;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    const int g = c / cpg;
+    gn_mean_rstd(stats, n, G, g, m, eps, mean, rstd);
+    double sb = 0, sc2 = 0;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+      sb += (double)gamma[k] * sums[((long long)n * C + k) * 2];
+      sc2 += (double)gamma[k] * sums[((long long)n * C + k) * 2 + 1];
+    }
+    s_mean[c] = mean; s_rstd[c] = rstd; s_g[c] = gamma[c]; s_b[c] = beta[c];
+    s_B[c] = (float)(sb / m) * rstd; s_C[c] = (float)(sc2 / m) * rstd;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = V * C8;
+  const bf16* dyn = dy + (long long)n * V * lddy;
+  const bf16* yn = y + (long long)n * V * ldy;
+  bf16* dxn = dx + (long long)n * V * lddx;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i / C8;
+    const int c0 = (int)(i - vox * C8) * 8;
+    float d[8], x[8], o[8];
+    unpack8(ldg16_stream(dyn + vox * lddy + c0), d);
+    unpack8(ldg16_stream(yn + vox * ldy + c0), x);
+    if (ACC) unpack8(ldg16(dxn + vox * lddx + c0), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - s_mean[c0 + j]) * s_rstd[c0 + j];
+      float dz = d[j];
+      if (RELU && fmaf(xh, s_g[c0 + j], s_b[c0 + j]) <= 0.f) dz = 0.f;
+      const float v = dz * s_g[c0 + j] * s_rstd[c0 + j] - s_B[c0 + j] - xh * s_C[c0 + j];
+      o[j] = ACC ? o[j] + v : v;
+    }
+    stg16(dxn + vox * lddx + c0, pack8(o));
+  }
+}
+
+// dgamma[c] = Σ_n sums[n][c][1], dbeta[c] = Σ_n sums[n][c][0]
+__global__ void gn_param_grad_kernel(const double* __restrict__ sums, int N, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0, b = 0;
+  for (int n = 0; n < N; ++n) { b += sums[((long long)n * C + c) * 2]; a += sums[((long long)n * C + c) * 2 + 1]; }
+  if (accumulate) { dgamma[c] += (float)a; dbeta[c] += (float)b; }
+  else { dgamma[c] = (float)a; dbeta[c] = (float)b; }
+}
+
+// out = a + b (bf16, pitched) — gradient accumulation of two branches
+__global__ void __launch_bounds__(GN_THREADS) add_kernel(const bf16* __restrict__ a, long long lda,
+                                                         const bf16* __restrict__ b, long long ldb, bf16* __restrict__ o,
+                                                         long long ldo, long long V, int C) {
+  const int C8 = C >> 3;
+  const long long total = V * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i / C8;
+    const int c0 = (int)(i - vox * C8) * 8;
+    float x[8], y[8];
+    unpack8(ldg16_stream(a + vox * lda + c0), x);
+    unpack8(ldg16_stream(b + vox * ldb + c0), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    stg16(o + vox * ldo + c0, pack8(x));
+  }
+}
+
+static int ew_blocks(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)b3d_num_sms() * 16;
+  return (int)std::max<long long>(1, std::min(b, cap));
+}
+
+extern "C" {
+
+int b3d_gn_apply(const void* y, long long ldy, const double* stats, const float* gamma, const float* beta, int G,
+                 int relu, int res_mode, const void* r, long long ldr, const double* stats_r, const float* gamma_r,
+                 const float* beta_r, int Gr, void* out, long long ldo, int N, long long V, int C, float eps,
+                 void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0, "gn_apply: bad C=%d G=%d", C, G);
+  B3D_REQUIRE(ldy % 8 == 0 && ldo % 8 == 0, "gn_apply: pitches must be multiples of 8");
+  B3D_REQUIRE(res_mode >= 0 && res_mode <= 2, "gn_apply: bad res_mode");
+  if (res_mode == 1) B3D_REQUIRE(C % Gr == 0, "gn_apply: bad Gr");
+  dim3 grid(ew_blocks(V * (C / 8), GN_THREADS * 2), N);
+  const size_t smem = 4 * (size_t)C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(RL, RS)                                                                                              \
+  gn_apply_kernel<RL, RS><<<grid, GN_THREADS, smem, st>>>((const bf16*)y, ldy, stats, gamma, beta, G, (const bf16*)r, ldr, \
+                                                          stats_r, gamma_r, beta_r, Gr, (bf16*)out, ldo, V, C, eps)
+  if (relu) { if (res_mode == 0) LAUNCH(true, 0); else if (res_mode == 1) LAUNCH(true, 1); else LAUNCH(true, 2); }
+  else { if (res_mode == 0) LAUNCH(false, 0); else if (res_mode == 1) LAUNCH(false, 1); else LAUNCH(false, 2); }
+#undef LAUNCH
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// sums: double [N][C][2], must be zeroed by the caller before the call (accumulated with atomics)
+int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const double* stats,
+                      const float* gamma, const float* beta, int G, int relu, double* sums, int N, long long V, int C,
+                      float eps, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0, "gn_bwd_reduce: bad C=%d G=%d", C, G);
+  const int per_sample = std::max(1, std::min(ew_blocks(V * (C / 8), GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
+  dim3 grid(per_sample, N);
+  const size_t smem = 6 * (size_t)C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (relu) gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps);
+  else gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const double* stats,
+                     const float* gamma, const float* beta, int G, int relu, const double* sums, void* dx,
+                     long long lddx, int accumulate, int N, long long V, int C, float eps, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0, "gn_bwd_apply: bad C=%d G=%d", C, G);
+  dim3 grid(ew_blocks(V * (C / 8), GN_THREADS * 2), N);
+  const size_t smem = 6 * (size_t)C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(RL, AC)                                                                                               \
+  gn_bwd_apply_kernel<RL, AC><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, \
+                                                              beta, G, sums, (bf16*)dx, lddx, V, C, eps)
+  if (relu) { if (accumulate) LAUNCH(true, true); else LAUNCH(true, false); }
+  else { if (accumulate) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_gn_param_grad(const double* sums, int N, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {
+  gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, N, C, dgamma, dbeta, accumulate);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+int b3d_add_bf16(const void* a, long long lda, const void* b, long long ldb, void* o, long long ldo, long long V, int C,
+                 void* stream) {
+  B3D_REQUIRE(C % 8 == 0, "add: C must be a multiple of 8");
+  add_kernel<<<ew_blocks(V * (C / 8), GN_THREADS * 2), GN_THREADS, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)o, ldo, V, C);
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+"""Thin Python wrappers over the C ABI of libb3d.so (one function per exported entry point).
+
+Conventions
+-----------
+* activations: torch.bfloat16 tensors of shape [N, D, H, W, C] (NDHWC).  A tensor may be a channel slice of a wider
+  buffer (e.g. half of a concat buffer): only stride(-1) == 1 and "voxel pitch" stride(3) (= ld, in elements) matter.
+* logits / loss tensors: torch.float32 [N, K, D, H, W] contiguous (the reference's NCDHW), targets int64 [N, D, H, W].
+* statistics: torch.float64 [N or 1, G, 2] = (sum, sum of squares) accumulated by the producing kernel.
+* everything is enqueued on the current CUDA stream; nothing here synchronises with the host.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import c_int, c_ll, c_sz, c_vp, check, ptr, stream_ptr
+
+c_float, c_double = ctypes.c_float, ctypes.c_double
+EPS = 1e-5
+
+
+def _L():
+    return _lib.lib()
+
+
+def roundup(a, b):
+    return (a + b - 1) // b * b
+
+
+def ld(t):
+    """voxel pitch (elements) of an NDHWC activation (possibly a channel slice)."""
+    assert t.dim() == 5 and t.stride(4) == 1, "expected NDHWC activation"
+    n, d, h, w, _ = t.shape
+    p = t.stride(3)
+    assert t.stride(2) == w * p and t.stride(1) == h * w * p and t.stride(0) == d * h * w * p, "non-dense voxel layout"
+    return p
+
+
+def new_act(n, d, h, w, c, device, zero=False):
+    f = torch.zeros if zero else torch.empty
+    return f((n, d, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weights
+# ---------------------------------------------------------------------------------------------------------------
+PACK_FPROP, PACK_DGRAD, PACK_CONVT_FPROP, PACK_CONVT_DGRAD = 0, 1, 2, 3
+
+
+def pack_weight(w, mode):
+    """fp32 reference-layout weight -> bf16 [K/8][taps][rows][8] (see conv_igemm.cu).  Returns (packed, Kp, rows)."""
+    w = w.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    if mode in (PACK_FPROP, PACK_DGRAD):
+        cout, cin = w.shape[0], w.shape[1]
+        ntaps = w.shape[2] * w.shape[3] * w.shape[4]
+        if mode == PACK_FPROP:
+            kp, rows = roundup(cin, 16), roundup(cout, 16)
+        else:
+            kp, rows = roundup(cout, 16), roundup(cin, 16)
+        ptaps = ntaps
+    else:
+        cin, cout = w.shape[0], w.shape[1]
+        ntaps = 8
+        if mode == PACK_CONVT_FPROP:
+            kp, rows = roundup(cin, 16), 8 * cout
+        else:
+            kp, rows = 8 * cout, roundup(cin, 16)
+        ptaps = 1
+    out = torch.empty((kp // 8) * ptaps * rows * 8, dtype=torch.bfloat16, device=w.device)
+    check(_L().b3d_pack_weight(c_int(mode), ptr(w), c_int(cout), c_int(cin), c_int(ntaps), ptr(out), c_int(kp), c_int(rows),
+                               stream_ptr()))
+    return out, kp, rows
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 convolutions
+# ---------------------------------------------------------------------------------------------------------------
+def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=False, out=None, cin=None):
+    """y = conv(x) (+bias); optional GroupNorm (per sample) or BatchNorm (stats_batch) partial sums of y.
+    `cin`: number of leading channels of x to contract over (multiple of 16; defaults to all)."""
+    n, d, h, w, c = x.shape
+    cin = c if cin is None else cin
+    dev = x.device
+    if out is None:
+        out = new_act(n, d, h, w, cout, dev)
+    stats = None
+    if groups:
+        stats = torch.zeros((1 if stats_batch else n, groups, 2), dtype=torch.float64, device=dev)
+    ws_bytes = n * d * h * w * cout * 4
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes <= (1 << 28) else None
+    check(_L().b3d_conv_fprop(ptr(x), c_ll(ld(x)), ptr(wpack), c_int(w_rows), ptr(bias), ptr(out), c_ll(ld(out)),
+                              c_int(n), c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), c_int(ks), ptr(stats),
+                              c_int(groups), c_int(1 if stats_batch else 0), ptr(ws), c_sz(ws_bytes if ws is not None else 0),
+                              ptr(_lib.err_flag(dev)), stream_ptr()))
+    return out, stats
+
+
+def convT2_fprop(x, wpack, bias, cout, out=None):
+    n, d, h, w, cin = x.shape
+    if out is None:
+        out = new_act(n, 2 * d, 2 * h, 2 * w, cout, x.device)
+    check(_L().b3d_convT2_fprop(ptr(x), c_ll(ld(x)), ptr(wpack), ptr(bias), ptr(out), c_ll(ld(out)), c_int(n), c_int(d),
+                                c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(_lib.err_flag(x.device)), stream_ptr()))
+    return out
+
+
+def convT2_dgrad(dy, wpack, w_rows, cin, out=None):
+    n, d2, h2, w2, cout = dy.shape
+    d, h, w = d2 // 2, h2 // 2, w2 // 2
+    dev = dy.device
+    if out is None:
+        out = new_act(n, d, h, w, cin, dev)
+    ws = torch.empty(n * d * h * w * cin, dtype=torch.float32, device=dev)
+    check(_L().b3d_convT2_dgrad(ptr(dy), c_ll(ld(dy)), ptr(wpack), c_int(w_rows), ptr(out), c_ll(ld(out)), c_int(n), c_int(d),
+                                c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(ws), c_sz(ws.numel() * 4),
+                                ptr(_lib.err_flag(dev)), stream_ptr()))
+    return out
+
+
+def conv_wgrad(x, dy, cin_real, cout, ks, dw=None, accumulate=False):
+    """fp32 weight gradient in the reference layout [Cout, Cin, k, k, k].  x may carry zero-padded channels beyond
+    cin_real (its whole channel extent is contracted, only the first cin_real rows are written)."""
+    n, d, h, w, cin = x.shape
+    dev = x.device
+    if dw is None:
+        dw = torch.empty((cout, cin_real, ks, ks, ks), dtype=torch.float32, device=dev)
+        accumulate = False
+    cout_pad = roundup(cout, 16)
+    assert dy.shape[-1] == cout and (cout_pad == cout or ld(dy) >= cout_pad), "dy must expose padded channels"
+    ws = torch.empty(ks ** 3 * cin * cout_pad, dtype=torch.float32, device=dev)
+    check(_L().b3d_conv_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
+                              c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cin_real), c_int(cout), c_int(ks), ptr(ws),
+                              c_sz(ws.numel() * 4), ptr(_lib.err_flag(dev)), stream_ptr()))
+    return dw
+
+
+def convT2_wgrad(x, dy, cin, cout, dw=None, accumulate=False):
+    """fp32 ConvTranspose3d(k2,s2) weight gradient [Cin, Cout, 2, 2, 2]; x coarse [N,D,H,W,Cin], dy fine [N,2D,2H,2W,Cout]."""
+    n, d, h, w, _ = x.shape
+    dev = x.device
+    if dw is None:
+        dw = torch.empty((cin, cout, 2, 2, 2), dtype=torch.float32, device=dev)
+        accumulate = False
+    ws = torch.empty(8 * cin * cout, dtype=torch.float32, device=dev)
+    check(_L().b3d_convT2_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
+                                c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(ws), c_sz(ws.numel() * 4),
+                                ptr(_lib.err_flag(dev)), stream_ptr()))
+    return dw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GroupNorm family
+# ---------------------------------------------------------------------------------------------------------------
+def _nvc(t):
+    n, d, h, w, c = t.shape
+    return n, d * h * w, c
+
+
+def gn_apply(y, stats, gamma, beta, groups, relu, res=None, res_stats=None, res_gamma=None, res_beta=None, res_groups=0,
+             out=None):
+    """out = act(GN(y)) [+ GN'(res) if res_stats is given, + res otherwise]."""
+    n, v, c = _nvc(y)
+    if out is None:
+        out = torch.empty_like(y, memory_format=torch.contiguous_format)
+    res_mode = 0 if res is None else (1 if res_stats is not None else 2)
+    check(_L().b3d_gn_apply(ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta), c_int(groups), c_int(1 if relu else 0),
+                            c_int(res_mode), ptr(res), c_ll(ld(res) if res is not None else 0), ptr(res_stats),
+                            ptr(res_gamma), ptr(res_beta), c_int(res_groups if res_groups else 1), ptr(out), c_ll(ld(out)),
+                            c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
+    return out
+
+
+def gn_bwd(dy, y, stats, gamma, beta, groups, relu, dx=None, accumulate=False, sums=None, want_param_grads=True):
+    """GroupNorm(+ReLU) backward.  Returns (dx, dgamma, dbeta).  If `sums` ([N][C][2] float64: Σdz, Σdz·x̂) is given the
+    reduction phase is skipped (a producer already computed it)."""
+    n, v, c = _nvc(y)
+    dev = y.device
+    if sums is None:
+        sums = torch.zeros((n, c, 2), dtype=torch.float64, device=dev)
+        check(_L().b3d_gn_bwd_reduce(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta),
+                                     c_int(groups), c_int(1 if relu else 0), ptr(sums), c_int(n), c_ll(v), c_int(c),
+                                     c_float(EPS), stream_ptr()))
+    if dx is None:
+        dx = torch.empty_like(y, memory_format=torch.contiguous_format)
+        accumulate = False
+    check(_L().b3d_gn_bwd_apply(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta), c_int(groups),
+                                c_int(1 if relu else 0), ptr(sums), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
+                                c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
+    dgamma = dbeta = None
+    if want_param_grads:
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        check(_L().b3d_gn_param_grad(ptr(sums), c_int(n), c_int(c), ptr(dgamma), ptr(dbeta), c_int(0), stream_ptr()))
+    return dx, dgamma, dbeta
+
+
+def add_bf16(a, b, out=None):
+    n, v, c = _nvc(a)
+    if out is None:
+        out = torch.empty_like(a, memory_format=torch.contiguous_format)
+    check(_L().b3d_add_bf16(ptr(a), c_ll(ld(a)), ptr(b), c_ll(ld(b)), ptr(out), c_ll(ld(out)), c_ll(n * v), c_int(c),
+                            stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pooling, layout, reductions
+# ---------------------------------------------------------------------------------------------------------------
+def pool_fwd(x, mask=None):
+    n, d, h, w, c = x.shape
+    out = new_act(n, d // 2, h // 2, w // 2, c, x.device)
+    check(_L().b3d_pool_fwd(ptr(x), c_ll(ld(x)), ptr(mask), ptr(out), c_ll(ld(out)), c_int(n), c_int(d), c_int(h), c_int(w),
+                            c_int(c), stream_ptr()))
+    return out
+
+
+def pool_bwd(x, mask, dy, dx=None, accumulate=False):
+    n, d, h, w, c = x.shape
+    if dx is None:
+        dx = new_act(n, d, h, w, c, x.device)
+        accumulate = False
+    check(_L().b3d_pool_bwd(ptr(x), c_ll(ld(x)), ptr(mask), ptr(dy), c_ll(ld(dy)), ptr(dx), c_ll(ld(dx)),
+                            c_int(1 if accumulate else 0), c_int(n), c_int(d), c_int(h), c_int(w), c_int(c), stream_ptr()))
+    return dx
+
+
+def to_ndhwc_bf16(x, cpad):
+    """fp32 NCDHW -> bf16 NDHWC with channels zero-padded to cpad."""
+    n, cin, d, h, w = x.shape
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    out = new_act(n, d, h, w, cpad, x.device)
+    check(_L().b3d_to_ndhwc_bf16(ptr(x), ptr(out), c_ll(cpad), c_int(n), c_int(cin), c_ll(d * h * w), c_int(cpad), stream_ptr()))
+    return out
+
+
+def to_ncdhw_f32(x):
+    n, d, h, w, c = x.shape
+    out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
+    check(_L().b3d_to_ncdhw_f32(ptr(x), c_ll(ld(x)), ptr(out), c_int(n), c_int(c), c_ll(d * h * w), stream_ptr()))
+    return out
+
+
+def channel_sum(x):
+    """float64 [N][C] = Σ over voxels."""
+    n, v, c = _nvc(x)
+    sums = torch.zeros((n, c), dtype=torch.float64, device=x.device)
+    check(_L().b3d_channel_sum(ptr(x), c_ll(ld(x)), ptr(sums), c_int(n), c_ll(v), c_int(c), stream_ptr()))
+    return sums
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# attention gate pieces
+# ---------------------------------------------------------------------------------------------------------------
+def gate_psi_fwd(g1r, x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi, bpsi):
+    n, v, f = _nvc(g1r)
+    dev = g1r.device
+    psi_raw = torch.empty((n, v), dtype=torch.float32, device=dev)
+    st_psi = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+    check(_L().b3d_gate_psi_fwd(ptr(g1r), ptr(x1r), ptr(st_g), ptr(st_x), ptr(gam_g), ptr(bet_g), ptr(gam_x), ptr(bet_x),
+                                ptr(wpsi), ptr(bpsi), ptr(psi_raw), ptr(st_psi), c_int(n), c_ll(v), c_int(f), c_float(EPS),
+                                stream_ptr()))
+    return psi_raw, st_psi
+
+
+def gate_se_fwd(xsum, v, w1, b1, w2, b2):
+    n, c = xsum.shape
+    dev = xsum.device
+    ca = torch.empty((n, c), dtype=torch.float32, device=dev)
+    z = torch.empty((n, c // 8), dtype=torch.float32, device=dev)
+    mean = torch.empty((n, c), dtype=torch.float32, device=dev)
+    check(_L().b3d_gate_se_fwd(ptr(xsum), c_ll(v), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(ca), ptr(z), ptr(mean), c_int(n),
+                               c_int(c), stream_ptr()))
+    return ca, z, mean
+
+
+def gate_apply_fwd(x, psi_raw, st_psi, gpsi, bpsi_n, ca, out):
+    n, v, c = _nvc(x)
+    check(_L().b3d_gate_apply_fwd(ptr(x), c_ll(ld(x)), ptr(psi_raw), ptr(st_psi), ptr(gpsi), ptr(bpsi_n), ptr(ca), ptr(out),
+                                  c_ll(ld(out)), c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
+    return out
+
+
+def gate_apply_bwd(dout, x, psi_raw, st_psi, gpsi, bpsi_n, ca, dx):
+    n, v, c = _nvc(x)
+    dev = x.device
+    dpsin = torch.empty((n, v), dtype=torch.float32, device=dev)
+    dca = torch.zeros((n, c), dtype=torch.float64, device=dev)
+    st_dpsi = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+    check(_L().b3d_gate_apply_bwd(ptr(dout), c_ll(ld(dout)), ptr(x), c_ll(ld(x)), ptr(psi_raw), ptr(st_psi), ptr(gpsi),
+                                  ptr(bpsi_n), ptr(ca), ptr(dx), c_ll(ld(dx)), ptr(dpsin), ptr(dca), ptr(st_dpsi), c_int(n),
+                                  c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
+    return dpsin, dca, st_dpsi
+
+
+def gate_se_bwd(dca, ca, z, mean, w1, w2, v):
+    n, c = ca.shape
+    dev = ca.device
+    dw1 = torch.zeros_like(w1, dtype=torch.float32).reshape(c // 8, c)
+    db1 = torch.zeros(c // 8, dtype=torch.float32, device=dev)
+    dw2 = torch.zeros_like(w2, dtype=torch.float32).reshape(c, c // 8)
+    db2 = torch.zeros(c, dtype=torch.float32, device=dev)
+    xadd = torch.empty((n, c), dtype=torch.float32, device=dev)
+    check(_L().b3d_gate_se_bwd(ptr(dca), ptr(ca), ptr(z), ptr(mean), ptr(w1), ptr(w2), c_ll(v), ptr(dw1), ptr(db1), ptr(dw2),
+                               ptr(db2), ptr(xadd), c_int(n), c_int(c), stream_ptr()))
+    return dw1, db1, dw2, db2, xadd
+
+
+def gate_psi_bwd(dpsin, psi_raw, st_psi, st_dpsi, gpsi, g1r, x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi):
+    n, v, f = _nvc(g1r)
+    dev = g1r.device
+    dz = torch.empty_like(g1r)
+    sums_g = torch.zeros((n, f, 2), dtype=torch.float64, device=dev)
+    sums_x = torch.zeros((n, f, 2), dtype=torch.float64, device=dev)
+    small = torch.zeros(f + 3, dtype=torch.float32, device=dev)  # dwpsi[f], dbpsi, dgpsi, dbpsi_n
+    check(_L().b3d_gate_psi_bwd(ptr(dpsin), ptr(psi_raw), ptr(st_psi), ptr(st_dpsi), ptr(gpsi), ptr(g1r), ptr(x1r), ptr(st_g),
+                                ptr(st_x), ptr(gam_g), ptr(bet_g), ptr(gam_x), ptr(bet_x), ptr(wpsi), ptr(dz), ptr(sums_g),
+                                ptr(sums_x), c_vp(small.data_ptr()), c_vp(small.data_ptr() + 4 * f),
+                                c_vp(small.data_ptr() + 4 * (f + 1)), c_vp(small.data_ptr() + 4 * (f + 2)), c_int(n), c_ll(v),
+                                c_int(f), c_float(EPS), stream_ptr()))
+    return dz, sums_g, sums_x, small[:f], small[f:f + 1], small[f + 1:f + 2], small[f + 2:f + 3]
+
+
+def add_channel_const(dx, xadd):
+    n, v, c = _nvc(dx)
+    check(_L().b3d_add_channel_const(ptr(dx), c_ll(ld(dx)), ptr(xadd), c_int(n), c_ll(v), c_int(c), stream_ptr()))
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# heads
+# ---------------------------------------------------------------------------------------------------------------
+def ds_head_fwd(x, w, b):
+    """x [N,D,H,W,C] -> low-res logits fp32 [N, D, H, W, 4] (float4 per voxel)."""
+    n, d, h, wd, c = x.shape
+    k = w.shape[0]
+    out = torch.empty((n, d, h, wd, k), dtype=torch.float32, device=x.device)
+    check(_L().b3d_ds_head_fwd(ptr(x), c_ll(ld(x)), ptr(w), ptr(b), ptr(out), c_ll(n * d * h * wd), c_int(c), c_int(k),
+                               stream_ptr()))
+    return out
+
+
+def ds_head_bwd(dl_planar, x, w, dx, accumulate):
+    """dl_planar fp32 [N,K,D,H,W] (low-res) ; accumulates into dx (bf16 NDHWC) ; returns (dW [K,C], db [K])."""
+    n, d, h, wd, c = x.shape
+    k = w.shape[0]
+    dw = torch.zeros((k, c), dtype=torch.float32, device=x.device)
+    db = torch.zeros(k, dtype=torch.float32, device=x.device)
+    check(_L().b3d_ds_head_bwd(ptr(dl_planar), ptr(x), c_ll(ld(x)), ptr(w), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
+                               ptr(dw), ptr(db), c_int(n), c_ll(d * h * wd), c_int(c), c_int(k), stream_ptr()))
+    return dw, db
+
+
+def trilinear_up_fwd(lo, size):
+    n, dl, hl, wl, k = lo.shape
+    d, h, w = size
+    out = torch.empty((n, k, d, h, w), dtype=torch.float32, device=lo.device)
+    check(_L().b3d_trilinear_up_fwd(ptr(lo), ptr(out), c_int(n), c_int(dl), c_int(hl), c_int(wl), c_int(d), c_int(h), c_int(w),
+                                    c_int(k), stream_ptr()))
+    return out
+
+
+def trilinear_up_bwd(dup, lo_size):
+    n, k, d, h, w = dup.shape
+    dl, hl, wl = lo_size
+    dup = dup.contiguous()
+    dlo = torch.empty((n, k, dl, hl, wl), dtype=torch.float32, device=dup.device)
+    tmp = torch.empty(n * k * d * h * wl + n * k * d * hl * wl, dtype=torch.float32, device=dup.device)
+    check(_L().b3d_trilinear_up_bwd(ptr(dup), ptr(dlo), ptr(tmp), c_int(n), c_int(dl), c_int(hl), c_int(wl), c_int(d), c_int(h),
+                                    c_int(w), c_int(k), stream_ptr()))
+    return dlo
+
+
+def final_bn_prepare(stats, count, train, running_mean, running_var, num_batches, momentum, update_running):
+    f2 = running_mean.numel()
+    bn = torch.empty(2 * f2, dtype=torch.float32, device=running_mean.device)
+    check(_L().b3d_final_bn_prepare(ptr(stats), c_double(float(count)), c_int(1 if train else 0), ptr(running_mean),
+                                    ptr(running_var), ptr(num_batches), c_float(momentum), c_float(EPS), ptr(bn), c_int(f2),
+                                    c_int(1 if update_running else 0), stream_ptr()))
+    return bn
+
+
+def final_head_fwd(h, bn, gamma, beta, w2, b2):
+    n, d, hh, w, f2 = h.shape
+    k = w2.shape[0]
+    out = torch.empty((n, k, d, hh, w), dtype=torch.float32, device=h.device)
+    check(_L().b3d_final_head_fwd(ptr(h), c_ll(ld(h)), ptr(bn), ptr(gamma), ptr(beta), ptr(w2), ptr(b2), ptr(out), c_int(n),
+                                  c_ll(d * hh * w), c_int(f2), c_int(k), stream_ptr()))
+    return out
+
+
+def final_head_bwd(dl, h, bn, gamma, beta, w2, train):
+    n, d, hh, w, f2 = h.shape
+    k = w2.shape[0]
+    dev = h.device
+    red = torch.zeros(2 * f2 + k * f2 + k, dtype=torch.float64, device=dev)
+    dh = torch.empty_like(h, memory_format=torch.contiguous_format)
+    dgamma = torch.empty(f2, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(f2, dtype=torch.float32, device=dev)
+    dw2 = torch.empty((k, f2), dtype=torch.float32, device=dev)
+    db2 = torch.empty(k, dtype=torch.float32, device=dev)
+    check(_L().b3d_final_head_bwd(ptr(dl), ptr(h), c_ll(ld(h)), ptr(bn), ptr(gamma), ptr(beta), ptr(w2), ptr(red),
+                                  c_int(1 if train else 0), ptr(dh), c_ll(ld(dh)), ptr(dgamma), ptr(dbeta), ptr(dw2), ptr(db2),
+                                  c_int(n), c_ll(d * hh * w), c_int(f2), c_int(k), stream_ptr()))
+    return dh, dgamma, dbeta, dw2, db2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# loss and metrics
+# ---------------------------------------------------------------------------------------------------------------
+def loss_cfg(w_dice=0.0, smooth=1e-5, w_focal=0.0, f_alpha=0.25, f_gamma=2.0, w_ce=0.0, w_boundary=0.0, w_tv=0.0,
+             tv_alpha=0.7, tv_beta=0.3, tv_smooth=1e-5):
+    return (ctypes.c_float * 11)(w_dice, smooth, w_focal, f_alpha, f_gamma, w_ce, w_boundary, w_tv, tv_alpha, tv_beta,
+                                 tv_smooth)
+
+
+def loss_fwd(logits, target, cfg):
+    """Returns (values[6] = total,dice,focal,boundary,ce,tversky ; saved tuple for loss_bwd)."""
+    n, k, d, h, w = logits.shape
+    dev = logits.device
+    logits = logits.contiguous()
+    target = target.contiguous()
+    prob = torch.empty_like(logits)
+    need_e = cfg[6] != 0.0
+    e = torch.empty_like(logits) if need_e else None
+    acc = torch.empty((n, 16), dtype=torch.float64, device=dev)
+    values = torch.empty(6, dtype=torch.float32, device=dev)
+    check(_L().b3d_loss_fwd(ptr(logits), ptr(target), cfg, ptr(prob), ptr(e), ptr(acc), ptr(values), c_int(n), c_int(k),
+                            c_int(d), c_int(h), c_int(w), stream_ptr()))
+    return values, (prob, e, target, acc)
+
+
+def loss_bwd(saved, cfg, gscale, wscale, shape):
+    prob, e, target, acc = saved
+    n, k, d, h, w = shape
+    dlogits = torch.empty(shape, dtype=torch.float32, device=prob.device)
+    check(_L().b3d_loss_bwd(ptr(prob), ptr(e), ptr(target), ptr(acc), cfg, ptr(gscale), c_float(wscale), ptr(dlogits), c_int(n),
+                            c_int(k), c_int(d), c_int(h), c_int(w), stream_ptr()))
+    return dlogits
+
+
+def confusion(logits, target=None, want_mask=False):
+    """(hist int64 [K,K] with H[pred,true], mask uint8 [N,D,H,W] or None) — exact integer counts."""
+    n, k, d, h, w = logits.shape
+    dev = logits.device
+    logits = logits.contiguous()
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    hist = torch.zeros((k, k), dtype=torch.int64, device=dev)
+    mask = torch.empty((n, d, h, w), dtype=torch.uint8, device=dev) if want_mask else None
+    tgt = target.contiguous() if target is not None else None
+    check(_L().b3d_confusion(ptr(logits), ptr(tgt), ptr(mask), ptr(hist), c_int(n), c_int(k), c_ll(d * h * w), stream_ptr()))
+    return hist, mask
+
+
+def voxel_counts(mask):
+    """mask uint8 [D,H,W] -> (per-class counts int64[4], per-slice (last axis) tumour counts int64[W])."""
+    d, h, w = mask.shape
+    mask = mask.contiguous()
+    cls = torch.zeros(4, dtype=torch.int64, device=mask.device)
+    sl = torch.zeros(w, dtype=torch.int64, device=mask.device)
+    check(_L().b3d_voxel_counts(ptr(mask), c_ll(d * h * w), c_int(w), ptr(cls), ptr(sl), stream_ptr()))
+    return cls, sl
