@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the same path
+
+Workload (BASELINE.json configs[2], "cfg 3"): one training step = forward + deep-supervised Dice/focal/boundary loss +
+backward (+ gradient all-reduce for N > 1) + AdamW step of the default-architecture enhanced 3D U-Net on a synthetic
+batch of 2 volumes per GPU, 4 x 128^3, bf16 compute / fp32 parameters.  value = N * 2 * 128^3 * K / time  [voxels/s].
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "3D U-Net train voxels/s (4ch 128^3) at 1/2/4/8 B200; inference volumes/s"
+FEATURES = [32, 64, 128, 256, 512]
+PER_GPU_BATCH = 2
+SIZE = 128
+TRAIN_FLOP_PER_VOXEL = 1532476.0   # conv FLOPs fprop+dgrad+wgrad per input voxel, default arch
+FWD_FLOP_PER_VOXEL = 513215.0
+
+
+def _peaks():
+    p = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            m = json.load(fh)
+        p.update({k: m[k] for k in ("bf16_tflops_sustained", "bf16_tflops", "hbm_gbs") if k in m})
+        p["src"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                  "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+            if self.stop_flag:
+                break
+        try:
+            p.kill()
+        except Exception:
+            pass
+
+    def summary(self):
+        self.stop_flag = True
+        time.sleep(0.25)
+        try:
+            self.proc.kill()
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own PyTorch CPU path (sliced classes when /root/reference is mounted,
+# else the pinned oracle restatement — the only places outside tests/ allowed to execute oracle/)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_train_steps(steps, warmup, size=64, batch=1):
+    from oracle import ref_slice
+    from oracle import unet3d_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y = O.make_inputs(batch, size, size, size, seed=0)
+    if ref_slice.available():
+        ns = ref_slice.load()
+        torch.manual_seed(0)
+        model = ns["UNet3D"](4, 4, features=list(FEATURES))
+        crit = ns["DeepSupervisionLoss3D"]()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
+        kind = "reference"
+
+        def step():
+            opt.zero_grad()
+            loss = crit(model(x), y)
+            loss.backward()
+            opt.step()
+            return float(loss)
+    else:
+        sd = O.make_state_dict(4, 4, FEATURES, seed=0)
+        params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+        sd.update(params)
+        masks = O.make_dropout_masks(batch, FEATURES, 0.2)
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=1e-4)
+        kind = "port"
+
+        def step():
+            opt.zero_grad()
+            main, deep, _ = O.unet_forward(x, sd, FEATURES, training=True, dropout_masks=masks)
+            loss = O.deep_supervision_loss(main, deep, y)
+            loss.backward()
+            opt.step()
+            return float(loss)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    vox = batch * size ** 3
+    return {"value": vox / dt, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": "%d x 4 x %d^3 crop of the 2x4x128^3 step (fwd+DS loss+bwd+AdamW, fp32, %d timed steps after %d warm-up)"
+                      % (batch, size, steps, warmup), "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_train_steps(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "voxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3 train step (default arch, DS loss, AdamW), CPU sample: " + cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import b3d  # noqa: F401
+    import unet3d_b200 as U
+    from unet3d_b200 import _lib, ops
+    from unet3d_b200.parallel import DataParallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    lib.b3d_launch_count.restype = __import__("ctypes").c_longlong
+
+    torch.manual_seed(0)
+    model = U.UNet3D(4, 4, features=list(FEATURES), dropout_rate=0.2).to(dev)
+    model.train()
+    crit = U.DeepSupervisionLoss3D()
+    net = DataParallel(model) if world > 1 else model
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = torch.randn(PER_GPU_BATCH, 4, SIZE, SIZE, SIZE, generator=g).pin_memory()
+    y_host = torch.randint(0, 4, (PER_GPU_BATCH, SIZE, SIZE, SIZE), generator=g).pin_memory()
+    xd, yd = x_host.to(dev), y_host.to(dev)
+
+    def step(xi, yi):
+        opt.zero_grad(set_to_none=True)
+        out = net(xi)
+        loss = crit(out, yi)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(xd, yd)
+    barrier()
+
+    # ---- timed region: device-resident inputs ---------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ops.PROFILE = []
+    l0 = lib.b3d_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(xd, yd)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.b3d_launch_count() - l0
+    prof, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.summary() if sampler else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    vox_per_step = world * PER_GPU_BATCH * SIZE ** 3
+    value = vox_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs, H2D inside the timed region, D2H of the loss ---------------------------------
+    barrier()
+    e0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        xi = x_host.to(dev, non_blocking=True)
+        yi = y_host.to(dev, non_blocking=True)
+        last = step(xi, yi).item()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e = {"value": vox_per_step * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
+           "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+           "ms_per_step": ms_e2e / args.steps, "last_loss": last}
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), from CUDA events inside the timed region ----
+    peaks = _peaks()
+    fam = {}
+    for name, flops, a, b in prof:
+        d = fam.setdefault(name, [0.0, 0.0, 0])
+        d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+    roof, fams = None, {}
+    for name, (fl, tms, cnt) in fam.items():
+        fams[name] = {"tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None, "ms_per_step": tms / args.steps,
+                      "launches_per_step": cnt / args.steps, "gflop_per_launch": fl / max(cnt, 1) / 1e9}
+    if "igemm" in fam:
+        fl, tms, cnt = fam["igemm"]
+        ach = fl / (tms * 1e-3) / 1e12
+        roof = {"kernel": "igemm_kernel (conv fprop/dgrad/convT, tcgen05)", "bound": "tensor", "achieved": ach,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
+                "traffic": None, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
+                "avg_launch_ms": tms / max(cnt, 1), "algorithmic_gflop_per_launch": fl / max(cnt, 1) / 1e9,
+                "share_of_step": tms / ms}
+
+    # ---- inference (cfg 2): batch 1, 4 x 128^3, eval mode ---------------------------------------------------------------
+    inference = None
+    if not args.no_inference:
+        model.eval()
+        x1 = xd[:1].contiguous()
+        with torch.no_grad():
+            for _ in range(3):
+                model(x1)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                model(x1)
+            e1.record()
+            barrier()
+        ims = e0.elapsed_time(e1) / args.steps
+        t = torch.tensor([ims], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ims = float(t.item())
+        inference = {"value": world * 1e3 / ims, "unit": "volumes/s", "ms_per_volume": ims,
+                     "config": "batch 1 per GPU, 4x128^3, eval, bf16",
+                     "conv_tflops": FWD_FLOP_PER_VOXEL * SIZE ** 3 / (ims * 1e-3) / 1e12}
+        model.train()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_train_steps(2, 1)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "cfg3: train step, batch 2/GPU, 4x128^3, default arch [32,64,128,256,512], dropout 0.2, "
+                                   "DeepSupervisionLoss3D(CombinedLoss3D), step = fwd+loss+bwd(+NCCL grad all-reduce)+fused AdamW",
+                       "global_batch": world * PER_GPU_BATCH, "parallelism": "dp%d" % world,
+                       "l2": "no explicit flush: one step streams >5 GB of activations (>> 126 MB L2)"},
+            "conv_tflops_whole_step": TRAIN_FLOP_PER_VOXEL * vox_per_step / world / (ms / args.steps * 1e-3) / 1e12,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams,
+            "inference": inference, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

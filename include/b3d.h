@@ -1,0 +1,127 @@
+/* b3d.h — C ABI of libb3d.so: the B200 (sm_100a) hot path of the enhanced 3D U-Net.
+ *
+ * Drop-in boundary.  The reference (Ruhul-sde/Segmentation-and-classification-of-brain-tumor-using-3D-UNet) is pure
+ * Python/PyTorch and has no FFI of its own: what it "binds" for this path are the ATen operators its nn.Modules
+ * dispatch to.  Each entry point below names the reference call site (file:line under /root/reference) whose ATen
+ * work it replaces.  Host code (segmentation-...-unet_b200/ops.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  All pointers are DEVICE pointers unless noted.
+ * Activations are NDHWC bf16 with a voxel pitch `ld*` in elements (so channel slices of a concat buffer are
+ * addressable); logits are fp32 NCDHW; targets int64.  Every call is enqueued on `stream` (a cudaStream_t) and returns
+ * immediately; 0 = success, negative = error (b3d_last_error_string()).  The library never allocates persistent device
+ * memory, never synchronises, never throws and never exits.  Non-sm_100 devices are an error, not a fallback.
+ */
+#ifndef B3D_H_
+#define B3D_H_
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int b3d_version(void);
+const char* b3d_last_error_string(void);             /* thread-local */
+int b3d_check_device(void);                          /* 0 iff current device is compute capability 10.x */
+long long b3d_launch_count(void);                    /* kernels launched by this library so far (process-wide) */
+
+/* ---- convolutions on tcgen05 tensor cores (conv_igemm.cu, conv_wgrad.cu) ----------------------------------- */
+/* weight repack fp32 reference layout -> bf16 [K/8][taps][rows][8].
+ * mode 0: nn.Conv3d fprop, 1: Conv3d dgrad (flipped+transposed), 2: ConvTranspose3d fprop, 3: ConvTranspose3d dgrad */
+int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void* out, int Kp, int rows, void* stream);
+/* nn.Conv3d(k=3,pad=1) main.py:130,216,219 and nn.Conv3d(k=1) main.py:229,252,258 (forward; with mode-1 weights: the
+ * data gradient autograd computes for them).  Optional (+=) GroupNorm/BatchNorm partial sums of the output. */
+int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
+                   int N, int D, int H, int W, int Cin, int Cout, int ks, double* stats, int groups, int stats_batch,
+                   void* ws, size_t ws_bytes, int* err_flag, void* stream);
+/* nn.ConvTranspose3d(2f,f,k=2,s=2) main.py:121,183 forward / data gradient */
+int b3d_convT2_fprop(const void* x, long long ldx, const void* wpack, const float* bias, void* y, long long ldy, int N,
+                     int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);
+int b3d_convT2_dgrad(const void* dy, long long lddy, const void* wpack, int w_rows, void* dx, long long lddx, int N, int D,
+                     int H, int W, int Cin, int Cout, void* ws, size_t ws_bytes, int* err_flag, void* stream);
+/* weight gradients (autograd convolution_backward of the same modules), fp32 in the reference layouts */
+int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy, float* dw, int accumulate, int N, int D,
+                   int H, int W, int Cin, int Cin_real, int Cout, int ks, float* ws, size_t ws_bytes, int* err_flag,
+                   void* stream);
+int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long lddy, float* dw, int accumulate, int N, int D,
+                     int H, int W, int Cin, int Cout, float* ws, size_t ws_bytes, int* err_flag, void* stream);
+
+/* ---- GroupNorm(+ReLU)(+residual) — nn.GroupNorm/nn.ReLU in DoubleConv3D, main.py:215-233,235-242 (norm.cu) -- */
+int b3d_gn_apply(const void* y, long long ldy, const double* stats, const float* gamma, const float* beta, int G,
+                 int relu, int res_mode, const void* r, long long ldr, const double* stats_r, const float* gamma_r,
+                 const float* beta_r, int Gr, void* out, long long ldo, int N, long long V, int C, float eps, void* stream);
+int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long ldy, const double* stats,
+                      const float* gamma, const float* beta, int G, int relu, double* sums, int N, long long V, int C,
+                      float eps, void* stream);
+int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const double* stats,
+                     const float* gamma, const float* beta, int G, int relu, const double* sums, void* dx,
+                     long long lddx, int accumulate, int N, long long V, int C, float eps, void* stream);
+int b3d_gn_param_grad(const double* sums, int N, int C, float* dgamma, float* dbeta, int accumulate, void* stream);
+int b3d_add_bf16(const void* a, long long lda, const void* b, long long ldb, void* o, long long ldo, long long V, int C,
+                 void* stream);
+
+/* ---- MaxPool3d(2,2)+Dropout3d main.py:109-110,173-174 ; input staging training.py:287 (pool_layout.cu) ------- */
+int b3d_pool_fwd(const void* x, long long ldx, const float* mask, void* out, long long ldo, int N, int D, int H, int W,
+                 int C, void* stream);
+int b3d_pool_bwd(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
+                 long long lddx, int accumulate, int N, int D, int H, int W, int C, void* stream);
+int b3d_to_ndhwc_bf16(const float* x, void* out, long long ldo, int N, int Cin, long long V, int Cpad, void* stream);
+int b3d_to_ncdhw_f32(const void* x, long long ldx, float* out, int N, int C, long long V, void* stream);
+int b3d_channel_sum(const void* x, long long ldx, double* sums, int N, long long V, int C, void* stream);
+
+/* ---- AttentionGate3D main.py:244-299 (gate.cu) ---------------------------------------------------------------- */
+int b3d_gate_psi_fwd(const void* g1r, const void* x1r, const double* st_g, const double* st_x, const float* gam_g,
+                     const float* bet_g, const float* gam_x, const float* bet_x, const float* wpsi, const float* bpsi,
+                     float* psi_raw, double* st_psi, int N, long long V, int F, float eps, void* stream);
+int b3d_gate_se_fwd(const double* xsum, long long V, const float* w1, const float* b1, const float* w2, const float* b2,
+                    float* ca, float* zbuf, float* meanbuf, int N, int C, void* stream);
+int b3d_gate_apply_fwd(const void* x, long long ldx, const float* psi_raw, const double* st_psi, const float* gpsi,
+                       const float* bpsi_n, const float* ca, void* out, long long ldo, int N, long long V, int C,
+                       float eps, void* stream);
+int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long long ldx, const float* psi_raw,
+                       const double* st_psi, const float* gpsi, const float* bpsi_n, const float* ca, void* dx,
+                       long long lddx, float* dpsin, double* dca, double* st_dpsi, int N, long long V, int C, float eps,
+                       void* stream);
+int b3d_gate_se_bwd(const double* dca, const float* ca, const float* zbuf, const float* meanbuf, const float* w1,
+                    const float* w2, long long V, float* dW1, float* db1, float* dW2, float* db2, float* xadd, int N, int C,
+                    void* stream);
+int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_psi, const double* st_dpsi,
+                     const float* gpsi, const void* g1r, const void* x1r, const double* st_g, const double* st_x,
+                     const float* gam_g, const float* bet_g, const float* gam_x, const float* bet_x, const float* wpsi,
+                     void* dz, double* sums_g, double* sums_x, float* dwpsi, float* dbpsi, float* dgpsi, float* dbpsi_n,
+                     int N, long long V, int F, float eps, void* stream);
+int b3d_add_channel_const(void* dx, long long lddx, const float* xadd, int N, long long V, int C, void* stream);
+
+/* ---- output heads: deep supervision main.py:137-140,164-171 ; final_conv main.py:129-134 (heads.cu) ----------- */
+int b3d_ds_head_fwd(const void* x, long long ldx, const float* w, const float* b, float* out, long long NV, int C, int K,
+                    void* stream);
+int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
+                    int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream);
+int b3d_trilinear_up_fwd(const float* lo, float* out, int N, int Dl, int Hl, int Wl, int D, int H, int W, int K,
+                         void* stream);
+int b3d_trilinear_up_bwd(const float* dup, float* dlo, float* tmp, int N, int Dl, int Hl, int Wl, int D, int H, int W,
+                         int K, void* stream);
+int b3d_final_bn_prepare(const double* stats, double count, int train, float* running_mean, float* running_var,
+                         long long* num_batches, float momentum, float eps, float* bn, int F2, int update_running,
+                         void* stream);
+int b3d_final_head_fwd(const void* h, long long ldh, const float* bn, const float* gamma, const float* beta,
+                       const float* w2, const float* b2, float* out, int N, long long V, int F2, int K, void* stream);
+int b3d_final_head_bwd(const float* dl, const void* h, long long ldh, const float* bn, const float* gamma,
+                       const float* beta, const float* w2, double* red, int train, void* dh, long long lddh,
+                       float* dgamma, float* dbeta, float* dW2, float* db2, int N, long long V, int F2, int K,
+                       void* stream);
+
+/* ---- losses losses.py:7-126, training.py:517-566 ; metrics training.py:351-364, main.py:470-474 (loss.cu) ----- */
+int b3d_loss_fwd(const float* logits, const long long* target, const float* cfg11, float* prob, float* E, double* acc,
+                 float* values, int N, int K, int D, int H, int W, void* stream);
+int b3d_loss_bwd(const float* prob, const float* E, const long long* target, const double* acc, const float* cfg11,
+                 const float* gscale, float wscale, float* dlogits, int N, int K, int D, int H, int W, void* stream);
+int b3d_confusion(const float* logits, const long long* target, unsigned char* mask, unsigned long long* hist, int N,
+                  int K, long long V, void* stream);
+int b3d_voxel_counts(const unsigned char* mask, long long V, int W, unsigned long long* cls, unsigned long long* slices,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B3D_H_ */

@@ -39,6 +39,7 @@ void b3d_set_error(const char* fmt, ...);
   } while (0)
 
 int b3d_num_sms();
+extern long long g_b3d_launches;  // kernels launched by the library (bench.py reports it)
 
 // ---------------------------------------------------------------------------------------------
 // Small device utilities

@@ -555,7 +555,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
             "split%d items%d smem%zu tmem%d\n",
             N, D, H, W, nmaps, chan_per_map, Cout, ks, mode, P.TD, P.TH, P.TW, P.KC, P.BN, P.MB, P.stages, P.acc_bufs,
             P.ksplit, P.num_items, smem, P.tmem_cols);
-  igemm_kernel<<<grid, IGEMM_THREADS, smem, stream>>>(P);
+  igemm_kernel<<<grid, IGEMM_THREADS, smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   if (split) {
     const int chunks = Cout / 8;
@@ -563,7 +563,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms * 8);
     // keep each block inside as few samples as possible
     igemm_finalize_kernel<<<blocks, 256, 0, stream>>>(ws, V, Cout, (long long)D * H * W, bias, out, ld_out, stats,
-                                                      cpg > 0 ? cpg : 16, stats_groups, stats_batch);
+                                                      cpg > 0 ? cpg : 16, stats_groups, stats_batch); ++g_b3d_launches;
     B3D_CHECK_CUDA(cudaGetLastError());
   }
   return B3D_OK;
@@ -581,7 +581,7 @@ int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void
   const int ptaps = (mode >= 2) ? 1 : ntaps;
   const long long total = (long long)(Kp / 8) * ptaps * rows * 8;
   int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, mode, Cout, Cin, ntaps, Kp, rows);
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, mode, Cout, Cin, ntaps, Kp, rows); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

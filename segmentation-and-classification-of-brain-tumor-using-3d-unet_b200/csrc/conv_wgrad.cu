@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const uint32_t accfull = yempty0 + 16;
   const uint32_t accempty = accfull + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 8 * 4 * 2 + 32 + 16);
+  volatile uint32_t* s_started = reinterpret_cast<volatile uint32_t*>(aux + 8 * 4 * 2 + 32 + 16 + 8);  // chains that received MMAs
   (void)y_end;
 
   if (threadIdx.x == 0) {
@@ -168,6 +169,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         const int rows = min(P.TH, P.H - y0);
         if (key != cur_key) {
           if (cur_key >= 0) {
+            *s_started = started;
+            __threadfence_block();
             umma_commit(accfull);
             mbar_wait(accempty, flushes & 1u, P.err, 13);
             tc_fence_after();
@@ -228,7 +231,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         }
         Q = Q0 + nz + P.xspan - 1;
       }
-      if (cur_key >= 0) umma_commit(accfull);
+      if (cur_key >= 0) {
+        *s_started = started;
+        __threadfence_block();
+        umma_commit(accfull);
+      }
     }
     __syncwarp();
   } else {
@@ -243,6 +250,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       if (cur_key >= 0) {
         mbar_wait(accfull, flushes & 1u, P.err, 16);
         tc_fence_after();
+        const uint32_t started = *s_started;  // chains without any MMA hold stale TMEM contents: skip them
         const KeyInfo k = decode_key(P, cur_key);
         const int khs = m / P.ci_blk;
         const int ci = k.cib * P.ci_blk + (m - khs * P.ci_blk);
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             uint32_t rr[16];
             tmem_ld16(trow + j0, rr);
             tmem_ld_wait();
-            if (row_ok) {
+            if (row_ok && ((started >> chain) & 1u)) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (k.cob * P.BN + j0 + j < P.Cout_pad) atomicAdd(dst + j0 + j, __uint_as_float(rr[j]));
@@ -436,7 +444,7 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
             "items%d (per cta %d) smem%zu tmem%d\n",
             N, D, H, W, Cin_use, Cout, ks, P.variant, P.plane_mode, P.ci_blk, P.G, P.BN, P.nchains, P.TH, P.TZ, P.num_keys,
             P.num_items, P.items_per_cta, smem, P.tmem_cols);
-  wgrad_kernel<<<grid2, WG_THREADS, smem, stream>>>(P);
+  wgrad_kernel<<<grid2, WG_THREADS, smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -462,12 +470,16 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
     const long long V = (long long)N * D * H * W;
     int ww = 128;
     while (ww > 16 && V % ww) ww /= 2;
-    B3D_REQUIRE(V % ww == 0, "conv_wgrad: voxel count %lld not a multiple of 16", V);
-    n = 1; d = 1; w = ww; h = (int)(V / ww);
-    if (h > 65536) {  // keep TMA coordinates small: fold rows into planes
-      int dd = 1;
-      while (h > 4096 && h % 2 == 0) { h /= 2; dd *= 2; }
-      d = dd;
+    if (V % ww == 0) {
+      n = 1; d = 1; w = ww; h = (int)(V / ww);
+      if (h > 65536) {  // keep TMA coordinates small: fold rows into planes
+        int dd = 1;
+        while (h > 4096 && h % 2 == 0) { h /= 2; dd *= 2; }
+        d = dd;
+      }
+    } else {  // tiny volumes (1^3 / 2^3 levels): one short K run in plane mode, zero padded to a multiple of 16
+      B3D_REQUIRE(V <= 256, "conv_wgrad: voxel count %lld is neither a multiple of 16 nor <= 256", V);
+      n = 1; d = 1; h = 1; w = (int)V;
     }
   }
   YView yv;
@@ -476,7 +488,7 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   if (rc) return rc;
   const long long total = (long long)ntaps * Cin_real * Cout;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate);
+  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -502,7 +514,7 @@ int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long ldd
   if (rc) return rc;
   const long long total = (long long)8 * Cin * Cout;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate);
+  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

@@ -5,6 +5,7 @@
 #include <mutex>
 
 static thread_local char g_err[1024] = "";
+long long g_b3d_launches = 0;
 
 void b3d_set_error(const char* fmt, ...) {
   va_list ap;
@@ -64,6 +65,7 @@ int b3d_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
 extern "C" {
 const char* b3d_last_error_string() { return g_err; }
 int b3d_version() { return 100; }
+long long b3d_launch_count() { return g_b3d_launches; }
 // 0 if the current device is sm_100 (B200); negative otherwise — callers must fail loudly, there is no fallback.
 int b3d_check_device() {
   int dev = 0, major = 0, minor = 0;

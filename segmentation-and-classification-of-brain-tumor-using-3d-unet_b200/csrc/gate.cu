@@ -396,7 +396,7 @@ int b3d_gate_psi_fwd(const void* g1r, const void* x1r, const double* st_g, const
   B3D_REQUIRE(F % 8 == 0 && F % 4 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_fwd: F=%d unsupported", F);
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
   gate_psi_fwd_kernel<<<grid, 256, 4 * F * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi, 0.f, bpsi, psi_raw, st_psi, V, F, eps);
+      (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi, 0.f, bpsi, psi_raw, st_psi, V, F, eps); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -404,7 +404,7 @@ int b3d_gate_psi_fwd(const void* g1r, const void* x1r, const double* st_g, const
 int b3d_gate_se_fwd(const double* xsum, long long V, const float* w1, const float* b1, const float* w2, const float* b2,
                     float* ca, float* zbuf, float* meanbuf, int N, int C, void* stream) {
   B3D_REQUIRE(C % 8 == 0 && C <= 4096, "gate_se_fwd: bad C");
-  gate_se_fwd_kernel<<<N, 256, (C + C / 8) * sizeof(float), (cudaStream_t)stream>>>(xsum, V, w1, b1, w2, b2, ca, zbuf, meanbuf, C);
+  gate_se_fwd_kernel<<<N, 256, (C + C / 8) * sizeof(float), (cudaStream_t)stream>>>(xsum, V, w1, b1, w2, b2, ca, zbuf, meanbuf, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -415,7 +415,7 @@ int b3d_gate_apply_fwd(const void* x, long long ldx, const float* psi_raw, const
   B3D_REQUIRE(C % 8 == 0 && C <= 4096, "gate_apply_fwd: bad C");
   dim3 grid(gt_blocks_per_sample(V * (C / 8), 512, N), N);
   gate_apply_fwd_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n,
-                                                                               ca, (bf16*)out, ldo, V, C, eps);
+                                                                               ca, (bf16*)out, ldo, V, C, eps); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -427,7 +427,7 @@ int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long lon
   B3D_REQUIRE(C % 8 == 0 && (pow2(C / 8) || (C / 8) % 32 == 0) && C <= 4096, "gate_apply_bwd: C=%d unsupported", C);
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
   gate_apply_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)dout, lddo, (const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n, ca, (bf16*)dx, lddx, dpsin, dca, st_dpsi, V, C, eps);
+      (const bf16*)dout, lddo, (const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n, ca, (bf16*)dx, lddx, dpsin, dca, st_dpsi, V, C, eps); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -436,7 +436,7 @@ int b3d_gate_se_bwd(const double* dca, const float* ca, const float* zbuf, const
                     const float* w2, long long V, float* dW1, float* db1, float* dW2, float* db2, float* xadd, int N, int C,
                     void* stream) {
   gate_se_bwd_kernel<<<N, 256, (2 * C + 2 * (C / 8)) * sizeof(float), (cudaStream_t)stream>>>(dca, ca, zbuf, meanbuf, w1, w2, V, dW1,
-                                                                                             db1, dW2, db2, xadd, C);
+                                                                                             db1, dW2, db2, xadd, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -450,8 +450,8 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
   gate_psi_bwd_kernel<<<grid, 256, 12 * F * sizeof(float), (cudaStream_t)stream>>>(
       dpsin, psi_raw, st_psi, st_dpsi, gpsi, (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi,
-      (bf16*)dz, sums_g, sums_x, dwpsi, dbpsi, V, F, eps);
-  gate_psi_norm_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st_dpsi, N, dgpsi, dbpsi_n);
+      (bf16*)dz, sums_g, sums_x, dwpsi, dbpsi, V, F, eps); ++g_b3d_launches;
+  gate_psi_norm_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st_dpsi, N, dgpsi, dbpsi_n); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -459,7 +459,7 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
 int b3d_add_channel_const(void* dx, long long lddx, const float* xadd, int N, long long V, int C, void* stream) {
   B3D_REQUIRE(C % 8 == 0 && C <= 4096, "add_channel_const: bad C");
   dim3 grid(gt_blocks_per_sample(V * (C / 8), 512, N), N);
-  add_channel_const_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((bf16*)dx, lddx, xadd, V, C);
+  add_channel_const_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((bf16*)dx, lddx, xadd, V, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

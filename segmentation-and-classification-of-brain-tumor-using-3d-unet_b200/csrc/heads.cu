@@ -390,7 +390,7 @@ int b3d_ds_head_fwd(const void* x, long long ldx, const float* w, const float* b
   B3D_REQUIRE(K == KCLS, "ds_head: only %d output classes supported (got %d)", KCLS, K);
   B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
   ds_head_fwd_kernel<<<hd_blocks(NV * 8, 256), 256, KCLS * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)x, ldx, w, b, (float4*)out, NV, C);
+      (const bf16*)x, ldx, w, b, (float4*)out, NV, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -401,10 +401,8 @@ int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* 
   B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
   const size_t smem = (2 * KCLS * C + KCLS) * sizeof(float);
   const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 4);
-  if (accumulate)
-    ds_head_bwd_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C);
-  else
-    ds_head_bwd_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C);
+  if (accumulate) { ds_head_bwd_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C); ++g_b3d_launches; }
+  else { ds_head_bwd_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C); ++g_b3d_launches; }
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -413,7 +411,7 @@ int b3d_trilinear_up_fwd(const float* lo, float* out, int N, int Dl, int Hl, int
                          void* stream) {
   B3D_REQUIRE(K == KCLS, "trilinear_up: only %d classes supported", KCLS);
   trilinear_up_fwd_kernel<<<hd_blocks((long long)N * D * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)lo, out, N, Dl, Hl, Wl, D, H, W);
+      (const float4*)lo, out, N, Dl, Hl, Wl, D, H, W); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -427,11 +425,11 @@ int b3d_trilinear_up_bwd(const float* dup, float* dlo, float* tmp, int N, int Dl
   float* t1 = tmp;
   float* t2 = tmp + NK * D * H * Wl;
   long long tot = NK * D * H * Wl;
-  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(dup, t1, NK * D * H, W, Wl, 1);
+  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(dup, t1, NK * D * H, W, Wl, 1); ++g_b3d_launches;
   tot = NK * D * Hl * Wl;
-  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(t1, t2, NK * D, H, Hl, Wl);
+  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(t1, t2, NK * D, H, Hl, Wl); ++g_b3d_launches;
   tot = NK * Dl * Hl * Wl;
-  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(t2, dlo, NK, D, Dl, (long long)Hl * Wl);
+  lerp_adjoint_kernel<<<hd_blocks(tot, 256), 256, 0, st>>>(t2, dlo, NK, D, Dl, (long long)Hl * Wl); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -441,7 +439,7 @@ int b3d_final_bn_prepare(const double* stats, double count, int train, float* ru
                          void* stream) {
   B3D_REQUIRE(F2 <= 64, "final_bn_prepare: F2 too large");
   final_bn_prepare_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(stats, count, train, running_mean, running_var, num_batches,
-                                                             momentum, eps, bn, F2, update_running);
+                                                             momentum, eps, bn, F2, update_running); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -458,7 +456,7 @@ int b3d_final_head_fwd(const void* h, long long ldh, const float* bn, const floa
   F2_DISPATCH(F2,
     (final_head_fwd_kernel<8><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V)),
     (final_head_fwd_kernel<16><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V)),
-    (final_head_fwd_kernel<32><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V)));
+    (final_head_fwd_kernel<32><<<blocks, 256, 0, st>>>((const bf16*)h, ldh, bn, gamma, beta, w2, b2, out, N, V))); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -475,12 +473,12 @@ int b3d_final_head_bwd(const float* dl, const void* h, long long ldh, const floa
   F2_DISPATCH(F2,
     (final_head_bwd_reduce_kernel<8><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V)),
     (final_head_bwd_reduce_kernel<16><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V)),
-    (final_head_bwd_reduce_kernel<32><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V)));
+    (final_head_bwd_reduce_kernel<32><<<rblocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, N, V))); ++g_b3d_launches;
   F2_DISPATCH(F2,
     (final_head_bwd_apply_kernel<8><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V)),
     (final_head_bwd_apply_kernel<16><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V)),
-    (final_head_bwd_apply_kernel<32><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V)));
-  final_head_param_grad_kernel<<<1, 128, 0, st>>>(red, F2, dgamma, dbeta, dW2, db2);
+    (final_head_bwd_apply_kernel<32><<<blocks, 256, 0, st>>>(dl, (const bf16*)h, ldh, bn, gamma, beta, w2, red, train, (bf16*)dh, lddh, N, V))); ++g_b3d_launches;
+  final_head_param_grad_kernel<<<1, 128, 0, st>>>(red, F2, dgamma, dbeta, dW2, db2); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

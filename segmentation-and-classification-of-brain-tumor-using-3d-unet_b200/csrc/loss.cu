@@ -290,9 +290,9 @@ int b3d_loss_fwd(const float* logits, const long long* target, const float* cfg1
   const long long V = (long long)D * H * W;
   B3D_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_STRIDE * N, st));
   dim3 grid(std::max(1, ls_blocks(V, 256) / std::max(1, N)), N);
-  loss_softmax_kernel<<<grid, 256, 0, st>>>(logits, target, prob, acc, V, cfg);
-  if (cfg.w_boundary != 0.f) loss_boundary_kernel<<<grid, 256, 0, st>>>(prob, target, E, acc, D, H, W);
-  loss_finalize_kernel<<<1, 32, 0, st>>>(acc, N, V, cfg, values);
+  loss_softmax_kernel<<<grid, 256, 0, st>>>(logits, target, prob, acc, V, cfg); ++g_b3d_launches;
+  if (cfg.w_boundary != 0.f) { loss_boundary_kernel<<<grid, 256, 0, st>>>(prob, target, E, acc, D, H, W); ++g_b3d_launches; }
+  loss_finalize_kernel<<<1, 32, 0, st>>>(acc, N, V, cfg, values); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -305,7 +305,7 @@ int b3d_loss_bwd(const float* prob, const float* E, const long long* target, con
   memcpy(&cfg, cfg11, sizeof(cfg));
   const long long V = (long long)D * H * W;
   dim3 grid(std::max(1, ls_blocks(V, 256) / std::max(1, N)), N);
-  loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, E, target, acc, gscale, wscale, dlogits, N, D, H, W, cfg);
+  loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, E, target, acc, gscale, wscale, dlogits, N, D, H, W, cfg); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -314,7 +314,7 @@ int b3d_loss_bwd(const float* prob, const float* E, const long long* target, con
 int b3d_confusion(const float* logits, const long long* target, unsigned char* mask, unsigned long long* hist, int N,
                   int K, long long V, void* stream) {
   B3D_REQUIRE(K == KC, "confusion: only %d classes supported (got %d)", KC, K);
-  confusion_kernel<<<ls_blocks((long long)N * V, 256), 256, 0, (cudaStream_t)stream>>>(logits, target, mask, hist, N, V);
+  confusion_kernel<<<ls_blocks((long long)N * V, 256), 256, 0, (cudaStream_t)stream>>>(logits, target, mask, hist, N, V); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -322,7 +322,7 @@ int b3d_confusion(const float* logits, const long long* target, unsigned char* m
 int b3d_voxel_counts(const unsigned char* mask, long long V, int W, unsigned long long* cls, unsigned long long* slices,
                      void* stream) {
   B3D_REQUIRE(W <= 4096, "voxel_counts: W too large");
-  voxel_count_kernel<<<ls_blocks(V, 256), 256, (KC + W) * sizeof(unsigned int), (cudaStream_t)stream>>>(mask, V, W, cls, slices);
+  voxel_count_kernel<<<ls_blocks(V, 256), 256, (KC + W) * sizeof(unsigned int), (cudaStream_t)stream>>>(mask, V, W, cls, slices); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

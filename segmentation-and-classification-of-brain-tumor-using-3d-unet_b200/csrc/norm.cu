@@ -253,8 +253,8 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
   dim3 grid(per_sample, N);
   const size_t smem = 6 * (size_t)C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  if (relu) gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps);
-  else gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps);
+  if (relu) { gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }
+  else { gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -277,7 +277,7 @@ int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ld
 }
 
 int b3d_gn_param_grad(const double* sums, int N, int C, float* dgamma, float* dbeta, int accumulate, void* stream) {
-  gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, N, C, dgamma, dbeta, accumulate);
+  gn_param_grad_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, N, C, dgamma, dbeta, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -286,7 +286,7 @@ int b3d_add_bf16(const void* a, long long lda, const void* b, long long ldb, voi
                  void* stream) {
   B3D_REQUIRE(C % 8 == 0, "add: C must be a multiple of 8");
   add_kernel<<<ew_blocks(V * (C / 8), GN_THREADS * 2), GN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)o, ldo, V, C);
+      (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)o, ldo, V, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

@@ -180,7 +180,7 @@ int b3d_pool_fwd(const void* x, long long ldx, const float* mask, void* out, lon
   B3D_REQUIRE(C % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "pool_fwd: need even dims and C%%8==0");
   const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
   pool_fwd_kernel<<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, mask, (bf16*)out, ldo, N,
-                                                                           D, H, W, C);
+                                                                           D, H, W, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -189,26 +189,22 @@ int b3d_pool_bwd(const void* x, long long ldx, const float* mask, const void* dy
                  long long lddx, int accumulate, int N, int D, int H, int W, int C, void* stream) {
   B3D_REQUIRE(C % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "pool_bwd: need even dims and C%%8==0");
   const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
-  if (accumulate)
-    pool_bwd_kernel<true><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, N, D, H, W, C);
-  else
-    pool_bwd_kernel<false><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, N, D, H, W, C);
+  if (accumulate) { pool_bwd_kernel<true><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>( (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, N, D, H, W, C); ++g_b3d_launches; }
+  else { pool_bwd_kernel<false><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>( (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, N, D, H, W, C); ++g_b3d_launches; }
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
 
 int b3d_to_ndhwc_bf16(const float* x, void* out, long long ldo, int N, int Cin, long long V, int Cpad, void* stream) {
   B3D_REQUIRE(Cpad % 8 == 0 && Cpad >= Cin, "to_ndhwc: bad Cpad");
-  to_ndhwc_kernel<<<ew_blocks2((long long)N * V, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)out, ldo, N, Cin, V, Cpad);
+  to_ndhwc_kernel<<<ew_blocks2((long long)N * V, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)out, ldo, N, Cin, V, Cpad); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
 
 int b3d_to_ncdhw_f32(const void* x, long long ldx, float* out, int N, int C, long long V, void* stream) {
   B3D_REQUIRE(C % 8 == 0, "to_ncdhw: C%%8");
-  to_ncdhw_kernel<<<ew_blocks2((long long)N * V, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, N, C, V);
+  to_ncdhw_kernel<<<ew_blocks2((long long)N * V, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, N, C, V); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -217,7 +213,7 @@ int b3d_channel_sum(const void* x, long long ldx, double* sums, int N, long long
   B3D_REQUIRE(C % 8 == 0 && C <= 4096, "channel_sum: bad C");
   const int per_sample = std::max(1, std::min(ew_blocks2(V * (C / 8), 256 * 8), b3d_num_sms() * 4 / std::max(1, N)));
   dim3 grid(per_sample, N);
-  channel_sum_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, ldx, sums, V, C);
+  channel_sum_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, ldx, sums, V, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

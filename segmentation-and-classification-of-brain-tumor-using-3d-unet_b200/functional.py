@@ -14,17 +14,14 @@ _PACK_CACHE = {}
 
 
 def packed(param, mode):
-    """bf16 tcgen05-ready copy of a conv weight, cached until the parameter is modified in place (optimizer step)."""
+    """bf16 tcgen05-ready copy of a conv weight, cached until the parameter is modified in place (optimizer step,
+    load_state_dict, .to(device)): keyed on the tensor's version counter and storage address."""
     key = (id(param), mode)
-    ver = param._version
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[1] is param.data.data_ptr() and hit[2].device == param.device:
-        return hit[2], hit[3], hit[4]
-    hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[1] == param.data_ptr():
+    if hit is not None and hit[0] == param._version and hit[1] == param.data_ptr():
         return hit[2], hit[3], hit[4]
     wp, kp, rows = ops.pack_weight(param, mode)
-    _PACK_CACHE[key] = (ver, param.data_ptr(), wp, kp, rows)
+    _PACK_CACHE[key] = (param._version, param.data_ptr(), wp, kp, rows)
     return wp, kp, rows
 
 

@@ -271,6 +271,10 @@ def test_confusion_and_voxel_counts_bit_exact():
     (2, 8, 8, 8, 32, 64, 3),       # small channels in plane mode
     (2, 8, 8, 16, 32, 16, 1),      # pointwise
     (1, 4, 4, 4, 256, 128, 1),     # pointwise, tiny volume
+    (1, 2, 2, 2, 256, 512, 3),     # 2^3 level of a 32^3 input
+    (2, 1, 1, 1, 512, 1024, 3),    # 1^3 bottleneck of a 32^3 input
+    (1, 2, 2, 2, 256, 128, 1),     # pointwise with 8 voxels
+    (1, 1, 1, 1, 512, 1024, 1),    # pointwise with a single voxel
 ])
 def test_conv_wgrad(n, d, h, w, cin, cout, ks):
     x = _bf(n, d, h, w, cin, seed=31)
@@ -297,7 +301,7 @@ def test_conv_wgrad_padded_input_channels():
     assert (dw - wt.grad).abs().max().item() <= 2e-3 * wt.grad.abs().max().item() + 1e-3
 
 
-@pytest.mark.parametrize("n,s,cin,cout", [(2, 4, 64, 32), (1, 8, 32, 16), (2, 16, 64, 32)])
+@pytest.mark.parametrize("n,s,cin,cout", [(2, 4, 64, 32), (1, 8, 32, 16), (2, 16, 64, 32), (1, 1, 512, 256), (2, 2, 256, 128)])
 def test_convT2_wgrad(n, s, cin, cout):
     x = _bf(n, s, s, s, cin, seed=35)
     dy = _bf(n, 2 * s, 2 * s, 2 * s, cout, seed=36)

@@ -1,0 +1,251 @@
+"""End-to-end parity of the B200 path (through the reference-shaped nn.Module API) against the oracle and the golden
+vectors produced by the reference itself.
+
+Stated tolerances (bf16 activations/weights, fp32 accumulation — north_star "bf16 relative tolerance"):
+  * logits          : relative L2 error <= 2.5e-2 vs the fp32 reference logits (reference's own bf16-autocast error: 1.25e-2)
+  * loss            : |delta| <= 1.5e-2 * |loss|
+  * gradients       : per-tensor cosine similarity >= 0.9 and relative L2 <= 0.35 for tensors carrying >= 1e-3 of the total
+                      gradient norm (the reference's own bf16-autocast gradients sit at median 0.145 / p90 0.29 rel-L2,
+                      SURVEY hard part 5); whole-model gradient cosine >= 0.99
+  * argmax / counts : bit-exact GIVEN IDENTICAL fp32 logits (kernel-level test); end-to-end agreement fraction >= 0.97
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import b3d  # noqa: F401
+    import unet3d_b200 as U
+    from unet3d_b200 import ops
+
+from oracle import unet3d_oracle as O
+
+DEV = "cuda:0"
+REPORT = {}
+
+
+def _rel_l2(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _cos(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _load(model, sd):
+    model.load_state_dict(sd)
+    return model.to(DEV)
+
+
+def _oracle_train(sd, x, y, feats, masks=None):
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    main, deep, bn = O.unet_forward(x, sdg, feats, training=True, dropout_masks=masks)
+    loss = O.deep_supervision_loss(main, deep, y)
+    loss.backward()
+    return main.detach(), [d.detach() for d in deep], float(loss), {k: v.grad for k, v in sdg.items()}, bn
+
+
+def _check_grads(model, ref_grads, tag):
+    tot = np.sqrt(sum(float(g.double().norm()) ** 2 for g in ref_grads.values() if g is not None))
+    dots = n1 = n2 = 0.0
+    worst = (1.0, 0.0, None)
+    for k, p in model.named_parameters():
+        rg = ref_grads[k]
+        if rg is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        g = p.grad.detach().cpu()
+        dots += float(g.double().reshape(-1) @ rg.double().reshape(-1))
+        n1 += float(g.double().norm()) ** 2
+        n2 += float(rg.double().norm()) ** 2
+        if float(rg.double().norm()) >= 1e-3 * tot:
+            c, r = _cos(g, rg), _rel_l2(g, rg)
+            if c < worst[0]:
+                worst = (c, r, k)
+            assert c >= 0.9 and r <= 0.35, "%s: grad cos %.4f rel-L2 %.4f" % (k, c, r)
+    total_cos = dots / (np.sqrt(n1 * n2) + 1e-30)
+    REPORT[tag + "_grad_total_cos"] = total_cos
+    REPORT[tag + "_grad_worst"] = worst
+    assert total_cos >= 0.99, total_cos
+
+
+@pytest.mark.parametrize("case", ["model_small", "model_small_n2"])
+def test_unet_eval_and_train_vs_golden_and_oracle(golden, golden_arrays, case):
+    rec = golden[case]
+    feats = tuple(rec["features"])
+    sd = O.make_state_dict(4, 4, feats, seed=rec["seed"])
+    x, y = O.make_inputs(rec["n"], rec["size"], rec["size"], rec["size"], seed=rec["seed"])
+    model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), sd)
+    xd, yd = x.to(DEV), y.to(DEV)
+    model.eval()
+    with torch.no_grad():
+        ev = model(xd)
+    assert ev.shape == (rec["n"], 4) + (rec["size"],) * 3 and ev.dtype == torch.float32
+    with torch.no_grad():
+        ev_ref, _, _ = O.unet_forward(x, sd, feats, training=False)
+    r = _rel_l2(ev.cpu(), ev_ref)
+    REPORT[case + "_eval_logits_rel_l2"] = r
+    assert r <= 2.5e-2, r
+    arrays = golden_arrays(case)
+    if "eval_logits" in arrays:  # the reference's own output
+        assert _rel_l2(ev.cpu(), torch.from_numpy(arrays["eval_logits"])) <= 2.5e-2
+    agree = float((ev.argmax(1).cpu() == ev_ref.argmax(1)).float().mean())
+    REPORT[case + "_argmax_agree"] = agree
+    assert agree >= 0.97, agree
+    assert abs(U.calculate_dice_score(ev, yd) - O.dice_score(ev.cpu(), y)) < 1e-7  # metric exact on identical logits
+    # ---- training step
+    model.train()
+    main, deep = model(xd)
+    assert isinstance(deep, list) and len(deep) == 4 and all(d.shape == main.shape for d in deep)
+    crit = U.DeepSupervisionLoss3D()
+    loss = crit((main, deep), yd)
+    loss.backward()
+    rmain, rdeep, rloss, rgrads, rbn = _oracle_train(sd, x, y, feats)
+    assert abs(rloss - rec["ds_loss"]) < 1e-4  # oracle == reference
+    REPORT[case + "_loss"] = (float(loss), rloss)
+    assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss), (float(loss), rloss)
+    assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
+    for i in range(4):
+        assert _rel_l2(deep[i].detach().cpu(), rdeep[i]) <= 2.5e-2, i
+    _check_grads(model, rgrads, case)
+    np.testing.assert_allclose(model.final_conv[1].running_mean.cpu().numpy(), rbn[0].detach().numpy(), rtol=2e-2, atol=2e-3)
+    np.testing.assert_allclose(model.final_conv[1].running_var.cpu().numpy(), rbn[1].detach().numpy(), rtol=2e-2, atol=2e-3)
+    assert int(model.final_conv[1].num_batches_tracked) == 1
+    print("REPORT", json.dumps({k: v for k, v in REPORT.items()}, default=str))
+
+
+def test_unet_dropout_uses_torch_rng_stream():
+    """Dropout3d parity: (a) the masks the model draws are the ones F.dropout3d would draw from the same generator state
+    (same op sequence on the torch CUDA generator), (b) with those masks the step matches the oracle."""
+    import torch.nn.functional as F
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(4, 4, feats, seed=3)
+    x, y = O.make_inputs(2, 32, 32, 32, seed=3)
+    model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.2), sd)
+    model.train()
+    torch.manual_seed(99)
+    ref_masks = [F.dropout3d(torch.ones(2, f, 2, 2, 2, device=DEV), 0.2, True)[:, :, 0, 0, 0].cpu() for f in feats]
+    torch.manual_seed(99)
+    main, deep = model(x.to(DEV))
+    masks = [m.cpu() for m in model._last_dropout_masks]
+    for a, b in zip(masks, ref_masks):
+        assert torch.equal(a, b)
+        assert set(a.unique().tolist()) <= {0.0, 1.25}
+    loss = U.DeepSupervisionLoss3D()((main, deep), y.to(DEV))
+    loss.backward()
+    rmain, rdeep, rloss, rgrads, _ = _oracle_train(sd, x, y, feats, masks=masks)
+    assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
+    assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss)
+    _check_grads(model, rgrads, "dropout")
+
+
+def test_default_architecture_train_step(golden):
+    rec = golden["model_default"]
+    feats = tuple(rec["features"])
+    sd = O.make_state_dict(4, 4, feats, seed=rec["seed"])
+    x, y = O.make_inputs(rec["n"], rec["size"], rec["size"], rec["size"], seed=rec["seed"])
+    model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), sd)
+    model.train()
+    main, deep = model(x.to(DEV))
+    loss = U.DeepSupervisionLoss3D()((main, deep), y.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - rec["ds_loss"]) <= 1.5e-2 * abs(rec["ds_loss"]), (float(loss), rec["ds_loss"])
+    for k, p in model.named_parameters():
+        g = rec["grads"][k]
+        if g is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+        elif g["l2"] > 1e-3:
+            got = float(p.grad.double().norm())
+            assert abs(got - g["l2"]) <= 0.35 * g["l2"], (k, got, g["l2"])
+
+
+def test_loss_modules_match_oracle():
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(2, 4, 16, 16, 16, generator=g) * 2
+    y = torch.randint(0, 4, (2, 16, 16, 16), generator=g)
+    ld_, yd = logits.to(DEV).requires_grad_(True), y.to(DEV)
+    tot, parts = U.CombinedLoss3D()(ld_, yd)
+    rt, rp = O.combined_loss3d(logits, y)
+    assert abs(float(tot) - float(rt)) < 2e-5
+    assert set(parts) == {"dice_loss", "focal_loss", "boundary_loss", "total_loss"}
+    for k in parts:
+        assert isinstance(parts[k], float) and abs(parts[k] - float(rp[k])) < 2e-5
+    assert abs(float(U.CombinedLoss()(ld_, yd)) - float(O.trainer_combined_loss(logits, y))) < 2e-5
+    assert abs(float(U.TverskyLoss3D()(ld_, yd)) - float(O.tversky_loss(logits, y))) < 2e-5
+    assert abs(float(U.DiceLoss()(ld_, yd)) - float(O.dice_loss(logits, y, 1e-6))) < 2e-5
+    assert abs(float(U.FocalLoss()(ld_, yd)) - float(O.focal_loss(logits, y, 1.0, 2.0))) < 2e-5
+    # tensor (eval-mode output) through the deep-supervision wrapper
+    assert abs(float(U.DeepSupervisionLoss3D()(ld_, yd)) - float(rt)) < 2e-5
+    lt = logits.clone().requires_grad_(True)
+    (O.trainer_combined_loss(lt, y) * 3.0).backward()
+    (U.CombinedLoss()(ld_, yd) * 3.0).backward()
+    assert (ld_.grad.cpu() - lt.grad).abs().max() <= 1e-4 * lt.grad.abs().max()
+
+
+def test_standalone_blocks_vs_reference_golden(golden_arrays):
+    arrays = golden_arrays("blocks")
+    sd = O.make_state_dict(16, 4, (32, 64, 128, 256, 512), seed=5)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 16, 8, 8, 8, generator=g)
+    dc = U.DoubleConv3D(16, 32)
+    dc.load_state_dict({k[len("downs.0."):]: v for k, v in sd.items() if k.startswith("downs.0.")})
+    dc = dc.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out = dc(xd)
+    assert _rel_l2(out.detach().cpu(), torch.from_numpy(arrays["doubleconv_out"])) <= 2.5e-2
+    out.square().mean().backward()
+    xr = x.clone().requires_grad_(True)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("downs.0.")}
+    O.double_conv(xr, sdo, "downs.0.").square().mean().backward()
+    assert _cos(xd.grad.cpu(), xr.grad) >= 0.98
+    for k, p in dc.named_parameters():
+        assert _cos(p.grad.cpu(), sdo["downs.0." + k].grad) >= 0.95, k
+    gg = torch.randn(2, 32, 8, 8, 8, generator=g)
+    xx = torch.randn(2, 32, 8, 8, 8, generator=g)
+    ag = U.AttentionGate3D(32, 32, 16)
+    ag.load_state_dict({k[len("ups.13."):]: v for k, v in sd.items() if k.startswith("ups.13.")})
+    ag = ag.to(DEV)
+    gd, xd2 = gg.to(DEV).requires_grad_(True), xx.to(DEV).requires_grad_(True)
+    out = ag(g=gd, x=xd2)
+    assert _rel_l2(out.detach().cpu(), torch.from_numpy(arrays["gate_out"])) <= 2.5e-2
+    out.square().mean().backward()
+    gr, xr2 = gg.clone().requires_grad_(True), xx.clone().requires_grad_(True)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("ups.13.")}
+    O.attention_gate(gr, xr2, sdo, "ups.13.").square().mean().backward()
+    assert _cos(xd2.grad.cpu(), xr2.grad) >= 0.98 and _cos(gd.grad.cpu(), gr.grad) >= 0.95
+    for k, p in ag.named_parameters():
+        rg = sdo["ups.13." + k].grad
+        if float(rg.abs().max()) < 1e-9:
+            assert float(p.grad.abs().max()) < 1e-5, k  # psi.0.bias: analytically zero (cancels in GroupNorm(1,1))
+        else:
+            assert _cos(p.grad.cpu(), rg) >= 0.95, (k, _cos(p.grad.cpu(), rg))
+
+
+def test_no_cpu_fallback():
+    m = U.UNet3D(4, 4, features=[16, 32, 64, 128, 256])
+    with pytest.raises(Exception):
+        m(torch.randn(1, 4, 32, 32, 32))
+    with pytest.raises(Exception):
+        U.CombinedLoss3D()(torch.randn(1, 4, 8, 8, 8), torch.zeros(1, 8, 8, 8, dtype=torch.long))
+    with pytest.raises(ValueError):
+        m.to(DEV)(torch.randn(1, 4, 24, 32, 32, device=DEV))
+
+
+def test_segment_and_volumes_bit_exact():
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(4, 4, feats, seed=7)
+    x, _ = O.make_inputs(1, 32, 32, 32, seed=7)
+    model = _load(U.UNet3D(4, 4, features=list(feats)), sd).eval()
+    mask, logits = U.segment(model, x.to(DEV), return_logits=True)
+    assert mask.dtype == torch.uint8 and torch.equal(mask.long().cpu(), logits.argmax(1).cpu())
+    vols = U.tumor_volumes(mask[0])
+    tumour, per_class, per_slice = O.voxel_counts(mask[0].cpu())
+    assert vols == {"tumor_voxels": tumour, "class_voxels": per_class, "slice_voxels": per_slice}
