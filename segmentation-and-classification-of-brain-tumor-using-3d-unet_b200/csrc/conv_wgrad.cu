@@ -343,8 +343,9 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
   P.tmem_cols = tc;
   B3D_REQUIRE(tc <= 512, "wgrad: TMEM overflow");
 
-  // tile rows
+  // tile rows (and, if even one row does not fit, a narrower N block)
   int TH;
+  long long guard = 0;
   if (P.plane_mode) {
     TH = H;
     const int BH = H + 2 * halo;
@@ -359,15 +360,23 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
     P.x_tx_bytes = (uint32_t)P.CI8 * BH * P.BW * 16;
     P.y_tx_bytes = (uint32_t)P.CO8 * H * P.BW * 16;
     B3D_REQUIRE(BH <= 256 && P.CI8 <= 256, "wgrad: plane too large");
+    guard = (long long)(16 - P.CI8) * P.XP * 16 + 1024;   // garbage M rows beyond the staged chunks
   } else {
-    TH = 1;
-    for (int cand = 16; cand >= 1; cand /= 2) {
-      if (cand > H && cand > 1) continue;
-      const int BH = (P.variant == 0) ? cand + 2 : cand;
-      const long long xs = ((long long)BH * P.CI8 * P.BW * 16 + 1023) / 1024 * 1024;
-      const long long ys = ((long long)cand * P.CO8 * W * 16 + 1023) / 1024 * 1024;
-      const long long guard = (long long)16 * P.BW * 16 * 2 + 4096;
-      if (P.R * xs + 2 * ys + guard + 256 <= kWgSmemBudget) { TH = cand; break; }
+    TH = 0;
+    while (TH == 0) {
+      for (int cand = 16; cand >= 1; cand /= 2) {
+        if (cand > H && cand > 1) continue;
+        const int BH = (P.variant == 0) ? cand + 2 : cand;
+        const long long xs = ((long long)BH * P.CI8 * P.BW * 16 + 1023) / 1024 * 1024;
+        const long long ys = ((long long)cand * P.CO8 * W * 16 + 1023) / 1024 * 1024;
+        const long long over = std::max<long long>(0, (long long)((cand - 1) * P.CI8 + 16 - BH * P.CI8) * P.BW * 16);
+        const long long g = std::max<long long>(0, over - 2 * ys) + 1024;
+        if (P.R * xs + 2 * ys + g + 256 <= kWgSmemBudget) { TH = cand; guard = g; break; }
+      }
+      if (TH == 0) {
+        B3D_REQUIRE(P.BN > 16, "wgrad: tile does not fit in shared memory (W=%d Cin=%d Cout=%d)", W, Cin_use, Cout);
+        P.BN /= 2; P.CO8 = P.BN / 8; P.n_cob = (Cout_pad + P.BN - 1) / P.BN;
+      }
     }
     P.BH = (P.variant == 0) ? TH + 2 : TH;
     P.ksteps = W / 16;
@@ -378,6 +387,7 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
     B3D_REQUIRE(P.BH <= 256, "wgrad: tile too tall");
   }
   P.TH = TH;
+  { int c2 = P.nchains * P.BN, t2 = 32; while (t2 < c2) t2 *= 2; P.tmem_cols = t2; }
   P.tiles_y = (H + TH - 1) / TH;
   if (P.variant == 0) P.num_keys = P.n_cib * P.n_cob;
   else if (P.variant == 1) P.num_keys = P.n_cib * P.n_cob * 9;
@@ -394,9 +404,7 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
   const int grid2 = (P.num_items + P.items_per_cta - 1) / P.items_per_cta;
   P.dwacc = dwacc; P.err = err_flag;
 
-  // guard: garbage M rows (16 chunks x SBO) may read beyond the last slot; keep it inside the allocation
-  const long long sbo_a = P.plane_mode ? (long long)P.XP * 16 : (long long)P.BW * 16;
-  const long long guard = 16 * sbo_a + 4096;
+  // guard: garbage M rows may read beyond the last slot; `guard` keeps those reads inside the allocation
   const size_t smem = (size_t)P.R * P.x_slot_bytes + 2 * (size_t)P.y_slot_bytes + 256 + (size_t)guard;
   B3D_REQUIRE(smem <= 227 * 1024, "wgrad: smem %zu too large (N%d D%d H%d W%d Cin%d Cout%d ks%d)", smem, N, D, H, W, Cin_use,
               Cout, ks);

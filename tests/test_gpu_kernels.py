@@ -275,6 +275,7 @@ def test_confusion_and_voxel_counts_bit_exact():
     (2, 1, 1, 1, 512, 1024, 3),    # 1^3 bottleneck of a 32^3 input
     (1, 2, 2, 2, 256, 128, 1),     # pointwise with 8 voxels
     (1, 1, 1, 1, 512, 1024, 1),    # pointwise with a single voxel
+    (1, 8, 32, 32, 512, 256, 1),   # wide pointwise: N block must shrink to fit shared memory
 ])
 def test_conv_wgrad(n, d, h, w, cin, cout, ks):
     x = _bf(n, d, h, w, cin, seed=31)
