@@ -143,8 +143,27 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       " [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// Warp-uniform leader election (elect.sync): role warps keep their control flow warp-uniform so that descriptors live
+// in uniform registers, and only the tcgen05 / TMA issue itself is predicated on the elected lane (the CUTLASS idiom).
+// A plain `if (lane == 0)` around the loops makes ptxas emit an ELECT/R2UR "waterfall" around every UTCHMMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // tcgen05 / TMEM
@@ -192,6 +211,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_hi(uint32_t sbo_bytes) {
   return (uint64_t)(((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14)) << 32;
 }
+// swizzled K-major descriptor high word: layout_type 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B (0 = none)
+__device__ __forceinline__ uint64_t umma_desc_hi_sw(uint32_t sbo_bytes, int layout_type) {
+  return umma_desc_hi(sbo_bytes) | ((uint64_t)layout_type << 61);
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint32_t lo = ((addr_bytes >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
   return umma_desc_hi(sbo_bytes) | lo;
@@ -206,4 +229,4 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N, int a_major, i
 // Host: TMA descriptor encode through the driver entry point (no -lcuda link dependency)
 // ---------------------------------------------------------------------------------------------
 int b3d_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box);
+                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle_bytes = 0);

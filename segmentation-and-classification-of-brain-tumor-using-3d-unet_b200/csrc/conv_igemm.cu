@@ -30,11 +30,12 @@ struct alignas(64) IgemmParams {
   int N, D, H, W;        // output-space extent covered by tiles
   int Cout;              // real number of output columns (per tap for pixel shuffle: P.ps_cout)
   int halo, ks;          // halo = ks/2 ; ks = 3 or 1
-  int TD, TH, TW, BD, BH, BW, box_vox, box_pitch;  // box_pitch = roundup(box_vox, 8): TMA smem dst must be 128 B aligned
+  int TD, TH, TW, BD, BH, BW, box_vox;
+  int RB, layout_type;   // smem row bytes (= KC*2: 32/64/128) and the matching UMMA swizzle layout type (6/4/2)
   int MB, BN, n_blocks, KC, k_chunks, chunks_per_map, stages, acc_bufs, acc_stride, tmem_cols;
   int tiles_x, tiles_y, tiles_z, num_tiles, num_items, ksplit, chunks_per_split;
   int row_mode, xblocks;   // row_mode: every M-block is one 128-wide run of a W row (no halo-gap rows)
-  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes;
+  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   int mode;              // 0 bf16 store, 1 fp32 atomic accumulate, 2 pixel-shuffle bf16 store
   bf16* out; long long ld_out;
   int ps_cout;           // pixel shuffle: channels per tap
@@ -104,13 +105,11 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
         for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(empty0 + 8 * s, ph ^ 1, P.err, 1);
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, P.a_tx_bytes + P.b_stage_bytes);
+          mbar_expect_tx(fb, P.a_tx_bytes + P.b_tx_bytes);
           const int map = kc / P.chunks_per_map;
           const int cbase = (kc - map * P.chunks_per_map) * P.KC;
-          const uint32_t dstA = sA + s * P.a_stage_bytes;
-          for (int j = 0; j < P.KC / 8; ++j)
-            tma_load_5d(dstA + j * P.box_pitch * 16, &P.tmA[map], fb, cbase + j * 8, x0, y0, z0, n);
-          tma_load_4d(sB + s * P.b_stage_bytes, &P.tmW, fb, 0, nblk * P.BN, 0, kc * (P.KC / 8));
+          tma_load_5d(sA + s * P.a_stage_bytes, &P.tmA[map], fb, cbase, x0, y0, z0, n);
+          tma_load_3d(sB + s * P.b_stage_bytes, &P.tmW, fb, kc * P.KC, nblk * P.BN, 0);
           if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
       }
@@ -120,10 +119,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
     // ======================= MMA issuer =======================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, P.BN, 0, 0);
-      const uint64_t hi = umma_desc_hi(128);
-      const uint32_t lboA = (uint32_t)P.box_pitch << 16;             // (box_pitch*16 B) >> 4, placed at bit 16
-      const uint32_t lboB = (uint32_t)(P.ks * P.ks * P.ks * P.BN) << 16;
-      const int ntaps = P.ks * P.ks * P.ks;
+      // K-major swizzled operands: rows of RB bytes, 8-row swizzle atoms (SBO = 8*RB), LBO unused (=1)
+      const uint64_t hi = umma_desc_hi_sw(8u * P.RB, P.layout_type);
+      const uint32_t rb16 = (uint32_t)P.RB >> 4;  // row pitch in 16-byte units
       uint32_t s = 0, ph = 0;
       int it = 0;
       for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
@@ -148,11 +146,13 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
             for (int kd = 0; kd < P.ks; ++kd)
               for (int kh = 0; kh < P.ks; ++kh)
                 for (int kw = 0; kw < P.ks; ++kw, ++tap) {
-                  const uint32_t aoff = a16 + mbase + (kd * P.BH + kh) * P.BW + kw;
-                  const uint32_t boff = b16 + tap * P.BN;
+                  // a tap shift is a ROW shift of the start address; the swizzle XOR uses absolute smem address bits
+                  // (scripts/umma_shift_test.cu), so any row offset is legal with base_offset = 0
+                  const uint32_t aoff = a16 + (uint32_t)(mbase + (kd * P.BH + kh) * P.BW + kw) * rb16;
+                  const uint32_t boff = b16 + (uint32_t)(tap * P.BN) * rb16;
                   for (int k16 = 0; k16 < P.KC / 16; ++k16) {
-                    const uint32_t alo = ((aoff + k16 * 2 * P.box_pitch) & 0x3FFFu) | lboA;
-                    const uint32_t blo = ((boff + k16 * 2 * ntaps * P.BN) & 0x3FFFu) | lboB;
+                    const uint32_t alo = ((aoff + k16 * 2) & 0x3FFFu) | (1u << 16);
+                    const uint32_t blo = ((boff + k16 * 2) & 0x3FFFu) | (1u << 16);
                     umma_bf16_ss(d, hi | alo, hi | blo, idesc, (kc > kc0 || tap > 0 || k16 > 0) ? 1u : 0u);
                   }
                 }
@@ -343,7 +343,7 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, long long V,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Weight packing: reference fp32 layouts -> bf16 [K/8][ntaps][rows][8]  (K-major 16-byte rows, ready for one TMA box)
+// Weight packing: reference fp32 layouts -> bf16 [ntaps][rows][Kp]  (K-major rows; one swizzled TMA box per K chunk)
 //   mode 0 conv fprop : W[co][ci][t]          -> k = ci, row = co, tap = t
 //   mode 1 conv dgrad : W[co][ci][t]          -> k = co, row = ci, tap = ntaps-1-t       (flipped + transposed)
 //   mode 2 convT fprop: Wt[ci][co][t8]        -> k = ci, row = t8*Cout+co, tap 0
@@ -352,14 +352,12 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, long long V,
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int mode, int Cout, int Cin,
                                    int ntaps, int Kp, int rows) {
   const int ptaps = (mode >= 2) ? 1 : ntaps;
-  const long long total = (long long)(Kp / 8) * ptaps * rows * 8;
+  const long long total = (long long)ptaps * rows * Kp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i & 7);
-    long long r = i >> 3;
-    const int row = (int)(r % rows); r /= rows;
-    const int t = (int)(r % ptaps);
-    const int c8 = (int)(r / ptaps);
-    const int k = c8 * 8 + j;
+    const int k = (int)(i % Kp);
+    long long r = i / Kp;
+    const int row = (int)(r % rows);
+    const int t = (int)(r / rows);
     float val = 0.f;
     if (mode == 0) {
       if (k < Cin && row < Cout) val = w[((long long)row * Cin + k) * ntaps + t];
@@ -416,20 +414,19 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
           const int BD = TD + 2 * halo, BH = TH + 2 * halo, BW = TW + 2 * halo;
           if (BD > 256 || BH > 256 || BW > 256) continue;
           const long long box_vox = (long long)BD * BH * BW;
-          const long long box_pitch = (box_vox + 7) / 8 * 8;
-          if (box_pitch * 16 >= 262144) continue;
+          const long long RB = KC * 2;
           const long long span = (long long)(TD - 1) * BH * BW + (long long)(TH - 1) * BW + TW;
           const bool row_mode = (TW % 128 == 0);
           const int MB = row_mode ? TD * TH * (TW / 128) : (int)((span + 127) / 128);
           if (MB * BN > 512) continue;
           const int acc_bufs = (2 * MB * BN <= 512) ? 2 : 1;
-          const long long a = box_pitch * KC * 2, b = (long long)ntaps * BN * KC * 2;
+          const long long a = (box_vox * RB + 1023) / 1024 * 1024, b = ((long long)ntaps * BN * RB + 1023) / 1024 * 1024;
           const int k_chunks = Ktotal / KC;
           int stages = (int)std::min<long long>(4, kSmemBudget / (a + b));
           if (stages < 1) continue;
           if (stages < 2) continue;
           const long long maxoff = (row_mode ? span : (long long)MB * 128) + (long long)(ks - 1) * (BH * BW + BW + 1);
-          const long long over = std::max<long long>(0, maxoff - box_vox) * 16;
+          const long long over = std::max<long long>(0, maxoff - box_vox) * RB;
           if (over > (long long)stages * b) continue;  // garbage rows must still read inside our smem
           const int n_blocks = (CoutPad + BN - 1) / BN;
           const long long tiles = (long long)N * ((D + TD - 1) / TD) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
@@ -499,7 +496,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   P.N = N; P.D = D; P.H = H; P.W = W; P.Cout = Cout; P.halo = halo; P.ks = ks;
   P.TD = pl.TD; P.TH = pl.TH; P.TW = pl.TW;
   P.BD = pl.TD + 2 * halo; P.BH = pl.TH + 2 * halo; P.BW = pl.TW + 2 * halo;
-  P.box_vox = P.BD * P.BH * P.BW; P.box_pitch = (P.box_vox + 7) / 8 * 8;
+  P.box_vox = P.BD * P.BH * P.BW;
   P.row_mode = (pl.TW % 128 == 0) ? 1 : 0; P.xblocks = pl.TW / 128;
   P.MB = pl.MB; P.BN = pl.BN; P.n_blocks = (CoutPad + pl.BN - 1) / pl.BN; P.KC = pl.KC;
   P.chunks_per_map = chan_per_map / pl.KC; P.k_chunks = P.chunks_per_map * nmaps;
@@ -511,7 +508,9 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   P.num_tiles = N * P.tiles_x * P.tiles_y * P.tiles_z;
   P.ksplit = pl.ksplit; P.chunks_per_split = (P.k_chunks + pl.ksplit - 1) / pl.ksplit;
   P.num_items = P.num_tiles * P.n_blocks * P.ksplit;
-  P.a_stage_bytes = (uint32_t)P.box_pitch * P.KC * 2; P.a_tx_bytes = (uint32_t)P.box_vox * P.KC * 2; P.b_stage_bytes = (uint32_t)ntaps * P.BN * P.KC * 2;
+  P.RB = P.KC * 2; P.layout_type = (P.RB == 128) ? 2 : (P.RB == 64 ? 4 : 6);
+  P.a_tx_bytes = (uint32_t)P.box_vox * P.RB; P.b_tx_bytes = (uint32_t)ntaps * P.BN * P.RB;
+  P.a_stage_bytes = (P.a_tx_bytes + 1023u) / 1024u * 1024u; P.b_stage_bytes = (P.b_tx_bytes + 1023u) / 1024u * 1024u;
   P.mode = mode; P.out = out; P.ld_out = ld_out; P.ps_cout = ps_cout; P.bias = bias;
   P.stats = stats; P.cpg = cpg > 0 ? cpg : 16; P.stats_groups = stats_groups; P.stats_batch = stats_batch;
   P.err = err_flag;
@@ -530,19 +529,19 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
     const ActView& v = views[m];
     uint64_t dims[5] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.D, (uint64_t)v.N};
     uint64_t strides[4] = {(uint64_t)v.sW, (uint64_t)v.sH, (uint64_t)v.sD, (uint64_t)v.sN};
-    uint32_t box[5] = {8, (uint32_t)P.BW, (uint32_t)P.BH, (uint32_t)P.BD, 1};
-    int rc = b3d_encode_tmap_bf16(&P.tmA[m], v.base, 5, dims, strides, box);
+    uint32_t box[5] = {(uint32_t)P.KC, (uint32_t)P.BW, (uint32_t)P.BH, (uint32_t)P.BD, 1};
+    int rc = b3d_encode_tmap_bf16(&P.tmA[m], v.base, 5, dims, strides, box, P.RB);
     if (rc) return rc;
   }
   {
     const int Kp = chan_per_map * nmaps;
-    uint64_t dims[4] = {8, (uint64_t)CoutPad, (uint64_t)ntaps, (uint64_t)(Kp / 8)};
-    uint64_t strides[3] = {16, (uint64_t)CoutPad * 16, (uint64_t)ntaps * CoutPad * 16};
-    uint32_t box[4] = {8, (uint32_t)P.BN, (uint32_t)ntaps, (uint32_t)(P.KC / 8)};
-    int rc = b3d_encode_tmap_bf16(&P.tmW, wpack, 4, dims, strides, box);
+    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)CoutPad, (uint64_t)ntaps};
+    uint64_t strides[2] = {(uint64_t)Kp * 2, (uint64_t)CoutPad * Kp * 2};
+    uint32_t box[3] = {(uint32_t)P.KC, (uint32_t)P.BN, (uint32_t)ntaps};
+    int rc = b3d_encode_tmap_bf16(&P.tmW, wpack, 3, dims, strides, box, P.RB);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 16 * P.stages + 48 + 64 * 4 + 128;
+  const size_t smem = (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 16 * P.stages + 48 + 64 * 4 + 128 + 1024;
   if (!g_smem_attr_set) {
     B3D_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_smem_attr_set = true;
@@ -577,9 +576,9 @@ extern "C" {
 int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void* out, int Kp, int rows,
                     void* stream) {
   B3D_REQUIRE(mode >= 0 && mode <= 3, "pack_weight: bad mode %d", mode);
-  B3D_REQUIRE(Kp % 8 == 0 && rows > 0, "pack_weight: bad Kp/rows");
+  B3D_REQUIRE(Kp % 16 == 0 && rows > 0, "pack_weight: bad Kp/rows");
   const int ptaps = (mode >= 2) ? 1 : ntaps;
-  const long long total = (long long)(Kp / 8) * ptaps * rows * 8;
+  const long long total = (long long)ptaps * rows * Kp;
   int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, mode, Cout, Cin, ntaps, Kp, rows); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
@@ -610,7 +609,11 @@ int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, 
   v.base = x; v.C = Cin; v.W = w; v.H = h; v.D = d; v.N = n;
   v.sW = ldx * 2; v.sH = v.sW * w; v.sD = v.sH * h; v.sN = v.sD * d;
   const int cpg = (stats && groups > 0) ? Cout / groups : 0;
-  if (stats) B3D_REQUIRE(ks == 3 || stats_batch || N == 1 || true, "unreachable");
+  if (ks == 3) {  // large planes, few output channels: input-stationary z-marching kernel (conv_zmarch.cu)
+    const int rc = b3d_try_zmarch(x, ldx, wpack, w_rows, bias, y, ldy, N, D, H, W, Cin, Cout, stats, cpg, groups, stats_batch,
+                                  err_flag, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   if (stats && ks == 1 && !stats_batch && N > 1) {
     // per-sample statistics need the sample index: keep N as the outer dim, flatten inside a sample
     long long V = (long long)D * H * W;

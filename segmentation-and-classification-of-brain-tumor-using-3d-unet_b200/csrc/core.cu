@@ -32,7 +32,7 @@ static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_encode_once;
 
 int b3d_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box) {
+                         const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -49,7 +49,12 @@ int b3d_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                    : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                                                           : CU_TENSOR_MAP_SWIZZLE_NONE)),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b3d_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu %llu box %u %u %u %u %u base %p",
