@@ -125,12 +125,18 @@ if __name__ == "__main__":
         allok &= conv_case(1, 4, 8, 64, 16, 16, 3, groups=16)
         allok &= convT_case(1, 4, 4, 4, 32, 16)
         allok &= convT_case(2, 8, 8, 8, 64, 32)
-    if which in ("all", "zm"):  # shapes that take the z-marching path (Cout <= 64, planes >= 4)
+    if which in ("all", "zs"):  # shapes that take the z-marching kd-stacked path (conv_zs.cu)
         allok &= conv_case(1, 8, 16, 128, 32, 32, 3)
         allok &= conv_case(2, 16, 8, 128, 64, 32, 3, bias=True)
         allok &= conv_case(1, 8, 12, 64, 16, 16, 3, groups=16)
-        allok &= conv_case(2, 5, 7, 32, 32, 64, 3)
+        allok &= conv_case(1, 8, 16, 64, 32, 16, 3, groups=8, bias=True)
+        allok &= conv_case(2, 5, 9, 40, 32, 64, 3)
         allok &= conv_case(1, 16, 16, 16, 64, 64, 3, bias=True)
+        allok &= conv_case(1, 6, 16, 24, 128, 64, 3)
+        allok &= conv_case(1, 7, 20, 16, 64, 128, 3)
+        allok &= conv_case(2, 3, 64, 64, 16, 32, 3)
+        allok &= conv_case(1, 40, 16, 16, 32, 32, 3)
+        allok &= conv_case(2, 2, 16, 16, 16, 64, 3)
     if which == "one":  # a single launch of the dominant layer shape, for ncu
         allok &= conv_case(2, 128, 128, 128, 32, 32, 3)
     if which == "one64":

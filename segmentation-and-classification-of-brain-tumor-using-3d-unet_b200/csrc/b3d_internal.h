@@ -4,8 +4,8 @@
 #include <string.h>
 
 #include <cuda_runtime.h>
-// conv_zmarch.cu: input-stationary 3x3x3 convolution for large planes / few output channels.
+// conv_zs.cu: z-marching, kd-stacked 3x3x3 convolution for large planes / few output channels.
 // Returns 0 if launched, 1 if the shape does not suit it (use the block-mode kernel), negative on error.
-int b3d_try_zmarch(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
+int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
                    int N, int D, int H, int W, int Cin, int Cout, double* stats, int cpg, int stats_groups,
                    int stats_batch, int* err_flag, cudaStream_t stream);

@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
                   // a tap shift is a ROW shift of the start address; the swizzle XOR uses absolute smem address bits
                   // (scripts/umma_shift_test.cu), so any row offset is legal with base_offset = 0
                   const uint32_t aoff = a16 + (uint32_t)(mbase + (kd * P.BH + kh) * P.BW + kw) * rb16;
-                  const uint32_t boff = b16 + (uint32_t)(tap * P.BN) * rb16;
+                  // packed tap order is (kh,kw,kd) for 3x3x3 (shared with conv_zs.cu, which stacks kd on N)
+                  const int tapB = (P.ks == 3) ? (kh * 3 + kw) * 3 + kd : tap;
+                  const uint32_t boff = b16 + (uint32_t)(tapB * P.BN) * rb16;
                   for (int k16 = 0; k16 < P.KC / 16; ++k16) {
                     const uint32_t alo = ((aoff + k16 * 2) & 0x3FFFu) | (1u << 16);
                     const uint32_t blo = ((boff + k16 * 2) & 0x3FFFu) | (1u << 16);
@@ -346,6 +348,8 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, long long V,
 // Weight packing: reference fp32 layouts -> bf16 [ntaps][rows][Kp]  (K-major rows; one swizzled TMA box per K chunk)
 //   mode 0 conv fprop : W[co][ci][t]          -> k = ci, row = co, tap = t
 //   mode 1 conv dgrad : W[co][ci][t]          -> k = co, row = ci, tap = ntaps-1-t       (flipped + transposed)
+//   (3x3x3: the packed tap index runs (kh,kw,kd) with kd fastest, so the three kd taps of one (kh,kw) are adjacent row
+//    blocks — conv_zs.cu multiplies them in ONE N = 3*Cout MMA)
 //   mode 2 convT fprop: Wt[ci][co][t8]        -> k = ci, row = t8*Cout+co, tap 0
 //   mode 3 convT dgrad: Wt[ci][co][t8]        -> k = t8*Cout+co, row = ci, tap 0
 // ---------------------------------------------------------------------------------------------
@@ -357,7 +361,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
     const int k = (int)(i % Kp);
     long long r = i / Kp;
     const int row = (int)(r % rows);
-    const int t = (int)(r / rows);
+    int t = (int)(r / rows);
+    if (ntaps == 27 && mode < 2) t = (t % 3) * 9 + t / 3;  // packed tap order (kh,kw,kd) -> reference order (kd,kh,kw)
     float val = 0.f;
     if (mode == 0) {
       if (k < Cin && row < Cout) val = w[((long long)row * Cin + k) * ntaps + t];
@@ -609,9 +614,9 @@ int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, 
   v.base = x; v.C = Cin; v.W = w; v.H = h; v.D = d; v.N = n;
   v.sW = ldx * 2; v.sH = v.sW * w; v.sD = v.sH * h; v.sN = v.sD * d;
   const int cpg = (stats && groups > 0) ? Cout / groups : 0;
-  if (ks == 3) {  // large planes, few output channels: input-stationary z-marching kernel (conv_zmarch.cu)
-    const int rc = b3d_try_zmarch(x, ldx, wpack, w_rows, bias, y, ldy, N, D, H, W, Cin, Cout, stats, cpg, groups, stats_batch,
-                                  err_flag, (cudaStream_t)stream);
+  if (ks == 3) {  // large planes, few output channels: z-marching kd-stacked kernel (conv_zs.cu)
+    const int rc = b3d_try_zs(x, ldx, wpack, w_rows, bias, y, ldy, N, D, H, W, Cin, Cout, stats, cpg, groups, stats_batch,
+                              err_flag, (cudaStream_t)stream);
     if (rc <= 0) return rc;
   }
   if (stats && ks == 1 && !stats_batch && N > 1) {
