@@ -7,71 +7,78 @@
 //
 // Design (B200-first, not a cuDNN translation):
 //   * voxels on UMMA-M (128 rows), output channels on UMMA-N, input channels x taps on K.
-//   * one TMA box load stages a HALO TILE of the activation ([BD][BH][BW] voxels x 8-channel chunks) in shared memory in
-//     the SWIZZLE_NONE "interleaved" K-major layout  [chunk][voxel][8 ch = 16 B].  In that layout a tap shift (kd,kh,kw)
-//     is just +((kd*BH+kh)*BW+kw)*16 B on the UMMA descriptor start address, so all 27 taps re-use the same staged bytes
-//     (no im2col, no per-tap reload from L2).  M-blocks are 128 consecutive positions of the halo-pitched linear index;
-//     rows that land in the halo gap are computed and discarded (128/130 useful at W=128).
-//   * weights are staged per K-chunk by ONE TMA box from the packed [K/8][tap][Cout][8] tensor.
-//   * accumulators live in TMEM (MB x BN fp32 columns, double-buffered when they fit) ; a single elected thread issues
-//     tcgen05.mma; 4 epilogue warps drain TMEM with tcgen05.ld, add bias, emit bf16 NDHWC (or fp32 split-K atomics, or the
-//     ConvTranspose pixel-shuffle scatter) and the per-(sample,group) sum / sum-of-squares the following GroupNorm /
-//     BatchNorm needs (so normalisation is a single read+write pass afterwards).
+//   * one TMA box load stages a HALO TILE of the activation ([TD][TH+2][TW+2] voxels x KC channels) in shared memory as
+//     K-major swizzled rows (one voxel = one row of KC*2 bytes).  A (kh,kw) tap is a ROW shift of the UMMA descriptor start
+//     address inside that tile (the swizzle XOR uses absolute smem address bits — scripts/umma_shift_test.cu), so the 9
+//     in-plane taps re-use the same staged bytes (no im2col); the kd taps are separate pipeline steps (box shifted in z).
+//   * an M-block is 16 groups of 8 consecutive x positions.  "patch" tiles (TH = 16a, TW = 8b) put the groups one tile row
+//     apart (descriptor SBO = row pitch) so every M row is a real voxel; "linear" tiles (small planes, 1x1x1 convs) use 128
+//     consecutive halo-pitched positions and discard the rows that fall into the halo gap.
+//   * weights: ONE TMA box per step from the packed [(kh,kw)][kd][Cout][K] tensor (the 9 (kh,kw) taps of this kd).
+//   * accumulators live in TMEM (MB x BN fp32 columns, double-buffered when they fit); the MMA loop is templated on
+//     (BN, KC) and unrolled so the single issuing thread spends a few uniform-datapath instructions per tcgen05.mma
+//     (scripts/umma_rate.cu: a naive loop costs ~300 clk per MMA, the MMA itself 40-128); 4 epilogue warps drain TMEM,
+//     add bias, emit bf16 NDHWC with 32-byte stores (or fp32 split-K atomics, or the ConvTranspose pixel-shuffle scatter)
+//     and accumulate the GroupNorm / BatchNorm sum / sum-of-squares in registers (flushed once per sample / channel block).
 //   * persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
 //     warps 2-5 = epilogue.
+//   * 3x3x3 layers with <= 64 output channels take the z-marching kd-stacked kernel in conv_zs.cu instead.
 #include "b3d_common.cuh"
 #include "b3d_internal.h"
 #include <algorithm>
 #include <math.h>
 
-struct alignas(64) IgemmParams {
+#define IG_THREADS 192
+#define IG_MAXMB 32
+#define IG_MAXSTAGES 8
+
+struct alignas(64) IgParams {
   CUtensorMap tmA[8];
   CUtensorMap tmW;
   int N, D, H, W;        // output-space extent covered by tiles
-  int Cout;              // real number of output columns (per tap for pixel shuffle: P.ps_cout)
-  int halo, ks;          // halo = ks/2 ; ks = 3 or 1
-  int TD, TH, TW, BD, BH, BW, box_vox;
-  int RB, layout_type;   // smem row bytes (= KC*2: 32/64/128) and the matching UMMA swizzle layout type (6/4/2)
-  int MB, BN, n_blocks, KC, k_chunks, chunks_per_map, stages, acc_bufs, acc_stride, tmem_cols;
-  int tiles_x, tiles_y, tiles_z, num_tiles, num_items, ksplit, chunks_per_split;
-  int row_mode, xblocks;   // row_mode: every M-block is one 128-wide run of a W row (no halo-gap rows)
-  uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
-  int mode;              // 0 bf16 store, 1 fp32 atomic accumulate, 2 pixel-shuffle bf16 store
+  int Cout;              // real number of output columns (pixel shuffle: 8 * ps_cout)
+  int halo, ks, KD;      // ks = 3 or 1 ; KD = ks (a pipeline step is one (K chunk, kd) pair)
+  int TD, TH, TW, BH, BW;
+  int MB, GS;            // M-blocks per tile ; M-block = 16 groups of 8 consecutive x positions, GS positions apart
+  int mb_base[IG_MAXMB]; // first position (halo-pitched linear index inside the staged box) of each M-block
+  int n_blocks, k_chunks, chunks_per_map, stages, acc_bufs, acc_stride, tmem_cols;
+  int tiles_x, tiles_y, tiles_z, num_tiles, num_items, ksplit, steps_total, steps_per_split;
+  uint32_t w_off, stage_bytes, a_tx, w_tx;
+  int mode;              // 0 bf16 store, 1 fp32 partial store into this split's workspace slice (split-K), 2 pixel-shuffle bf16 store
   bf16* out; long long ld_out;
   int ps_cout;           // pixel shuffle: channels per tap
   const float* bias;
-  float* out_f32; long long ld_f32;
+  float* out_f32; long long ld_f32; long long slice_f32;  // split-K partials: [ksplit][V][ld_f32]
   double* stats; int cpg; int stats_groups; int stats_batch;
   int* err;
 };
 
-#define IGEMM_THREADS 192
-
-// first halo-pitched linear position covered by M-block mb
-__device__ __forceinline__ int mblock_base(const IgemmParams& P, int mb) {
-  if (!P.row_mode) return mb * 128;
-  const int xb = mb % P.xblocks;
-  const int t = mb / P.xblocks;
-  const int py = t % P.TH, pz = t / P.TH;
-  return (pz * P.BH + py) * P.BW + xb * 128;
+__device__ __forceinline__ void stg32(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
-__global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_constant__ IgemmParams P) {
+// BN: output columns per item (UMMA N) ; KC: channels per pipeline step (smem row = KC*2 bytes = swizzle span)
+template <int BN, int KC>
+__global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IgParams P) {
+  constexpr int RB = KC * 2;
+  constexpr int NK16 = KC / 16;
+  constexpr uint32_t rb16 = RB / 16;
+  constexpr int LT = (RB == 128) ? 2 : (RB == 64 ? 4 : 6);
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = P.stages;
   const uint32_t sA = smem_u32(smem);
-  const uint32_t sB = sA + S * P.a_stage_bytes;
-  uint8_t* aux = smem + (size_t)S * (P.a_stage_bytes + P.b_stage_bytes);
+  uint8_t* aux = smem + (size_t)S * P.stage_bytes;
   const uint32_t full0 = smem_u32(aux);
-  const uint32_t empty0 = full0 + 8 * S;
-  const uint32_t tfull0 = empty0 + 8 * S;
+  const uint32_t empty0 = full0 + 8 * IG_MAXSTAGES;
+  const uint32_t tfull0 = empty0 + 8 * IG_MAXSTAGES;
   const uint32_t tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * S + 32);
-  float* s_stats = reinterpret_cast<float*>(aux + 16 * S + 48);  // [64]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * IG_MAXSTAGES + 32);
+  float* s_stats = reinterpret_cast<float*>(aux + 16 * IG_MAXSTAGES + 48);  // [64]
 
   if (threadIdx.x == 0) {
-    if (sA & 127u) { if (P.err) atomicExch(P.err, 9); __trap(); }  // TMA destinations need 128 B alignment
+    if (sA & 1023u) { if (P.err) atomicExch(P.err, 9); __trap(); }
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
     mbar_fence_init();
@@ -87,114 +94,160 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int m = 0; m * P.chunks_per_map < P.k_chunks; ++m) tma_prefetch_desc(&P.tmA[m]);
       tma_prefetch_desc(&P.tmW);
-      uint32_t s = 0, ph = 0;
-      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
-        const int tile = item / items_per_tile;
-        const int rem = item - tile * items_per_tile;
-        const int split = rem / P.n_blocks, nblk = rem - split * P.n_blocks;
-        int t = tile;
-        const int tx = t % P.tiles_x; t /= P.tiles_x;
-        const int ty = t % P.tiles_y; t /= P.tiles_y;
-        const int tz = t % P.tiles_z; const int n = t / P.tiles_z;
-        const int x0 = tx * P.TW - P.halo, y0 = ty * P.TH - P.halo, z0 = tz * P.TD - P.halo;
-        const int kc0 = split * P.chunks_per_split;
-        const int kc1 = min(P.k_chunks, kc0 + P.chunks_per_split);
-        for (int kc = kc0; kc < kc1; ++kc) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1, P.err, 1);
+    }
+    uint32_t s = 0, ph = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x) {
+      const int tile = item / items_per_tile;
+      const int rem = item - tile * items_per_tile;
+      const int split = rem / P.n_blocks, nblk = rem - split * P.n_blocks;
+      int t = tile;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y; t /= P.tiles_y;
+      const int tz = t % P.tiles_z; const int n = t / P.tiles_z;
+      const int x0 = tx * P.TW - P.halo, y0 = ty * P.TH - P.halo, z0 = tz * P.TD - P.halo;
+      const int st0 = split * P.steps_per_split;
+      const int st1 = min(P.steps_total, st0 + P.steps_per_split);
+      int kc = st0 / P.KD, kd = st0 - kc * P.KD;
+      for (int st = st0; st < st1; ++st) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1, P.err, 1);
+        if (elect_one()) {
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, P.a_tx_bytes + P.b_tx_bytes);
+          mbar_expect_tx(fb, P.a_tx + P.w_tx);
           const int map = kc / P.chunks_per_map;
-          const int cbase = (kc - map * P.chunks_per_map) * P.KC;
-          tma_load_5d(sA + s * P.a_stage_bytes, &P.tmA[map], fb, cbase, x0, y0, z0, n);
-          tma_load_3d(sB + s * P.b_stage_bytes, &P.tmW, fb, kc * P.KC, nblk * P.BN, 0);
-          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+          const int cbase = (kc - map * P.chunks_per_map) * KC;
+          const uint32_t dst = sA + s * P.stage_bytes;
+          tma_load_5d(dst, &P.tmA[map], fb, cbase, x0, y0, z0 + kd, n);
+          tma_load_4d(dst + P.w_off, &P.tmW, fb, kc * KC, nblk * BN, kd, 0);
         }
+        __syncwarp();
+        if (++kd == P.KD) { kd = 0; ++kc; }
+        if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, P.BN, 0, 0);
-      // K-major swizzled operands: rows of RB bytes, 8-row swizzle atoms (SBO = 8*RB), LBO unused (=1)
-      const uint64_t hi = umma_desc_hi_sw(8u * P.RB, P.layout_type);
-      const uint32_t rb16 = (uint32_t)P.RB >> 4;  // row pitch in 16-byte units
-      uint32_t s = 0, ph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
-        const int rem = item % items_per_tile;
-        const int split = rem / P.n_blocks;
-        const int kc0 = split * P.chunks_per_split;
-        const int kc1 = min(P.k_chunks, kc0 + P.chunks_per_split);
-        const int a = it % P.acc_bufs;
-        const uint32_t aph = (uint32_t)(it / P.acc_bufs) & 1u;
-        mbar_wait(tempty0 + 8 * a, aph ^ 1, P.err, 2);
+    // ======================= MMA issuer (warp-uniform control flow, one elected lane issues) =======================
+    const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    const uint64_t hiA = umma_desc_hi_sw((uint32_t)P.GS * RB, LT) | (1ull << 16);
+    const uint64_t hiB = umma_desc_hi_sw(8u * RB, LT) | (1ull << 16);
+    const uint32_t row_a = (uint32_t)P.BW * rb16;          // one tile row (kh step) in 16-byte units
+    const uint32_t row_b = (uint32_t)(P.ks * BN) * rb16;   // one kh step of the weight stage
+    uint32_t s = 0, ph = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
+      const int rem = item % items_per_tile;
+      const int split = rem / P.n_blocks;
+      const int st0 = split * P.steps_per_split;
+      const int st1 = min(P.steps_total, st0 + P.steps_per_split);
+      const int a = it % P.acc_bufs;
+      const uint32_t aph = (uint32_t)(it / P.acc_bufs) & 1u;
+      mbar_wait(tempty0 + 8 * a, aph ^ 1, P.err, 2);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + a * P.acc_stride;
+      for (int st = st0; st < st1; ++st) {
+        mbar_wait(full0 + 8 * s, ph, P.err, 3);
         tc_fence_after();
-        const uint32_t dbase = tmem_base + a * P.acc_stride;
-        for (int kc = kc0; kc < kc1; ++kc) {
-          mbar_wait(full0 + 8 * s, ph, P.err, 3);
-          tc_fence_after();
-          const uint32_t a16 = (sA + s * P.a_stage_bytes) >> 4;
-          const uint32_t b16 = (sB + s * P.b_stage_bytes) >> 4;
-          for (int mb = 0; mb < P.MB; ++mb) {
-            const uint32_t d = dbase + mb * P.BN;
-            const int mbase = mblock_base(P, mb);
-            int tap = 0;
-            for (int kd = 0; kd < P.ks; ++kd)
-              for (int kh = 0; kh < P.ks; ++kh)
-                for (int kw = 0; kw < P.ks; ++kw, ++tap) {
-                  // a tap shift is a ROW shift of the start address; the swizzle XOR uses absolute smem address bits
-                  // (scripts/umma_shift_test.cu), so any row offset is legal with base_offset = 0
-                  const uint32_t aoff = a16 + (uint32_t)(mbase + (kd * P.BH + kh) * P.BW + kw) * rb16;
-                  // packed tap order is (kh,kw,kd) for 3x3x3 (shared with conv_zs.cu, which stacks kd on N)
-                  const int tapB = (P.ks == 3) ? (kh * 3 + kw) * 3 + kd : tap;
-                  const uint32_t boff = b16 + (uint32_t)(tapB * P.BN) * rb16;
-                  for (int k16 = 0; k16 < P.KC / 16; ++k16) {
-                    const uint32_t alo = ((aoff + k16 * 2) & 0x3FFFu) | (1u << 16);
-                    const uint32_t blo = ((boff + k16 * 2) & 0x3FFFu) | (1u << 16);
-                    umma_bf16_ss(d, hi | alo, hi | blo, idesc, (kc > kc0 || tap > 0 || k16 > 0) ? 1u : 0u);
+        const uint32_t a16 = (sA + s * P.stage_bytes) >> 4;
+        const uint32_t b16 = a16 + (P.w_off >> 4);
+        const uint32_t first = (st == st0) ? 0u : 1u;
+        for (int mb = 0; mb < P.MB; ++mb) {
+          const uint32_t d = dbase + mb * BN;
+          uint32_t arow = a16 + (uint32_t)P.mb_base[mb] * rb16;
+          uint32_t brow = b16;
+          if (elect_one()) {
+            for (int kh = 0; kh < P.ks; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                if (kw < P.ks) {
+#pragma unroll
+                  for (int k = 0; k < NK16; ++k) {
+                    const uint32_t alo = arow + (uint32_t)(kw * rb16 + k * 2);
+                    const uint32_t blo = brow + (uint32_t)(kw * BN * rb16 + k * 2);
+                    umma_bf16_ss(d, hiA | alo, hiB | blo, idesc, (kh | kw | k) ? 1u : first);
                   }
                 }
+              }
+              arow += row_a;
+              brow += row_b;
+            }
           }
-          umma_commit(empty0 + 8 * s);
-          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+          __syncwarp();
         }
-        umma_commit(tfull0 + 8 * a);
+        if (elect_one()) umma_commit(empty0 + 8 * s);
+        __syncwarp();
+        if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) umma_commit(tfull0 + 8 * a);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ======================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =======================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;  // 0..127
     const int plane = P.BH * P.BW;
-    const int seglen = P.cpg < 16 ? P.cpg : 16;
+    const int cpg = P.cpg;
+    // statistics granule (channels per per-thread accumulator): 16, 4 or 1 — the host guarantees BN / granule <= 16
+    const int gran = cpg >= 16 ? 16 : (cpg >= 4 ? 4 : 1);
+    float a1[16], a2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
+    int cur_n = -1, cur_n0 = 0;
+    auto flush_stats = [&]() {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i * gran < BN) {
+          const float s1 = warp_sum(a1[i]), s2 = warp_sum(a2[i]);
+          if (lane == 0) {
+            const int gl = (cur_n0 + i * gran) / cpg - cur_n0 / cpg;  // group slot local to this n-block
+            atomicAdd(&s_stats[2 * gl], s1);
+            atomicAdd(&s_stats[2 * gl + 1], s2);
+          }
+        }
+        a1[i] = 0.f; a2[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int groups_blk = (cur_n0 + BN - 1) / cpg - cur_n0 / cpg + 1;
+      if (et < 2 * groups_blk) {
+        const int g = cur_n0 / cpg + (et >> 1);
+        if (g < P.stats_groups) {
+          const int ns = P.stats_batch ? 0 : cur_n;
+          atomicAdd(P.stats + ((long long)ns * P.stats_groups + g) * 2 + (et & 1), (double)s_stats[et]);
+        }
+        s_stats[et] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     int it = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
       const int tile = item / items_per_tile;
       const int rem = item - tile * items_per_tile;
       const int nblk = rem % P.n_blocks;
+      const int split = rem / P.n_blocks;
       int t = tile;
       const int tx = t % P.tiles_x; t /= P.tiles_x;
       const int ty = t % P.tiles_y; t /= P.tiles_y;
       const int tz = t % P.tiles_z; const int n = t / P.tiles_z;
       const int a = it % P.acc_bufs;
       const uint32_t aph = (uint32_t)(it / P.acc_bufs) & 1u;
+      const int n0 = nblk * BN;
+      if (P.stats != nullptr && (n != cur_n || n0 != cur_n0)) {
+        if (cur_n >= 0) flush_stats();
+        cur_n = n; cur_n0 = n0;
+      }
       mbar_wait(tfull0 + 8 * a, aph, P.err, 4);
       tc_fence_after();
-      const int n0 = nblk * P.BN;
+      const int cmax = (P.mode == 2 ? P.ps_cout : P.Cout);
       for (int mb = 0; mb < P.MB; ++mb) {
-        const int p = mblock_base(P, mb) + row;
+        const int p = P.mb_base[mb] + (row >> 3) * P.GS + (row & 7);
         const int pz = p / plane, pr = p - pz * plane;
         const int py = pr / P.BW, px = pr - py * P.BW;
         const int z = tz * P.TD + pz, y = ty * P.TH + py, x = tx * P.TW + px;
         const bool valid = (pz < P.TD) && (py < P.TH) && (px < P.TW) && (z < P.D) && (y < P.H) && (x < P.W);
         long long vox;
-        int ch_base = 0;
+        int ch_base;
         if (P.mode == 2) {
           const int t8 = n0 / P.ps_cout;
           ch_base = n0 - t8 * P.ps_cout;
@@ -204,45 +257,60 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
           ch_base = n0;
           vox = (((long long)n * P.D + z) * P.H + y) * P.W + x;
         }
-        const uint32_t trow = tmem_base + a * P.acc_stride + mb * P.BN + ((uint32_t)(q * 32) << 16);
-        for (int j0 = 0; j0 < P.BN; j0 += 16) {
+        const uint32_t trow = tmem_base + a * P.acc_stride + mb * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int j0 = 0; j0 < BN; j0 += 16) {
           uint32_t r[16];
           tmem_ld16(trow + j0, r);
           tmem_ld_wait();
           float v[16];
           const int c0 = ch_base + j0;
-          const int cmax = (P.mode == 2 ? P.ps_cout : P.Cout);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float f = __uint_as_float(r[j]);
             if (P.bias != nullptr && c0 + j < cmax) f += __ldg(P.bias + c0 + j);
             v[j] = f;
           }
-          if (P.stats != nullptr) {
-            for (int sg = 0; sg < 16; sg += seglen) {
-              float s1 = 0.f, s2 = 0.f;
-              if (valid) {
-                for (int j = sg; j < sg + seglen; ++j)
-                  if (c0 + j < cmax) { s1 += v[j]; s2 += v[j] * v[j]; }
-              }
-              s1 = warp_sum(s1); s2 = warp_sum(s2);
-              if (lane == 0) {
-                const int g = (n0 + j0 + sg) / P.cpg - n0 / P.cpg;  // group slot local to this n-block
-                atomicAdd(&s_stats[2 * g], s1);
-                atomicAdd(&s_stats[2 * g + 1], s2);
+          if (valid) {
+            if (P.stats != nullptr) {
+              if (gran == 16) {
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { s1 += v[j]; s2 += v[j] * v[j]; }
+                a1[j0 / 16] += s1; a2[j0 / 16] += s2;
+              } else if (gran == 4) {
+                if (j0 < 64) {
+#pragma unroll
+                  for (int qd = 0; qd < 4; ++qd) {
+                    const int ai = (j0 / 4 + qd) & 15;
+                    a1[ai] += (v[4 * qd] + v[4 * qd + 1]) + (v[4 * qd + 2] + v[4 * qd + 3]);
+                    a2[ai] += (v[4 * qd] * v[4 * qd] + v[4 * qd + 1] * v[4 * qd + 1]) +
+                              (v[4 * qd + 2] * v[4 * qd + 2] + v[4 * qd + 3] * v[4 * qd + 3]);
+                  }
+                }
+              } else if (j0 == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { a1[j] += v[j]; a2[j] += v[j] * v[j]; }
               }
             }
-          }
-          if (valid) {
             if (P.mode == 1) {
-              float* o = P.out_f32 + vox * P.ld_f32 + c0;
+              float* o = P.out_f32 + split * P.slice_f32 + vox * P.ld_f32 + c0;
+              if (c0 + 16 <= cmax) {
+                const uint4* pv = reinterpret_cast<const uint4*>(v);
+                stg32(o, pv[0], pv[1]);
+                stg32(o + 8, pv[2], pv[3]);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < cmax) atomicAdd(o + j, v[j]);
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < cmax) o[j] = v[j];
+              }
             } else {
               bf16* o = P.out + vox * P.ld_out + c0;
-              if (c0 + 8 <= cmax) stg16(o, pack8(v));
-              if (c0 + 16 <= cmax) stg16(o + 8, pack8(v + 8));
+              if (c0 + 16 <= cmax && ((reinterpret_cast<uintptr_t>(o) & 31) == 0)) stg32(o, pack8(v), pack8(v + 8));
+              else {
+                if (c0 + 8 <= cmax) stg16(o, pack8(v));
+                if (c0 + 16 <= cmax) stg16(o + 8, pack8(v + 8));
+              }
             }
           }
         }
@@ -250,21 +318,8 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * a);
-      if (P.stats != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int groups_blk = (n0 + P.BN - 1) / P.cpg - n0 / P.cpg + 1;
-        if (et < 2 * groups_blk) {
-          const int g = n0 / P.cpg + (et >> 1);
-          if (g < P.stats_groups) {
-            const float val = s_stats[et];
-            const int ns = P.stats_batch ? 0 : n;
-            atomicAdd(P.stats + ((long long)ns * P.stats_groups + g) * 2 + (et & 1), (double)val);
-          }
-          s_stats[et] = 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
     }
+    if (P.stats != nullptr && cur_n >= 0) flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -274,7 +329,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 1) igemm_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------
 // split-K finalize: fp32 workspace [V][Cout] -> (+bias) -> bf16 out (pitch ld_out) + GroupNorm/BatchNorm partial sums
 // ---------------------------------------------------------------------------------------------
-__global__ void igemm_finalize_kernel(const float* __restrict__ ws, long long V, int Cout, long long vox_per_sample,
+__global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, long long V, int Cout, long long vox_per_sample,
                                       const float* __restrict__ bias, bf16* __restrict__ out, long long ld_out,
                                       double* __restrict__ stats, int cpg, int stats_groups, int stats_batch) {
   __shared__ float s_acc[2 * 64];
@@ -294,8 +349,14 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, long long V,
     float v[8];
     if (act) {
       vox = idx / chunks; c8 = (int)(idx - vox * chunks);
-      const float4 a = *reinterpret_cast<const float4*>(ws + vox * Cout + c8 * 8);
-      const float4 b = *reinterpret_cast<const float4*>(ws + vox * Cout + c8 * 8 + 4);
+      float4 a = *reinterpret_cast<const float4*>(ws + vox * Cout + c8 * 8);
+      float4 b = *reinterpret_cast<const float4*>(ws + vox * Cout + c8 * 8 + 4);
+      for (int sp = 1; sp < nsplit; ++sp) {
+        const float* w2 = ws + (long long)sp * V * Cout + vox * Cout + c8 * 8;
+        const float4 a2 = *reinterpret_cast<const float4*>(w2);
+        const float4 b2 = *reinterpret_cast<const float4*>(w2 + 4);
+        a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+      }
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
       if (bias)
         for (int j = 0; j < 8; ++j) v[j] += bias[c8 * 8 + j];
@@ -385,84 +446,104 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
 static const int kSmemBudget = 227 * 1024 - 2048;
 
 struct IgemmPlan {
-  int TD, TH, TW, KC, BN, MB, stages, acc_bufs, ksplit;
+  int TD, TH, TW, KC, BN, MB, GS, stages, acc_bufs, ksplit, patch;
+  long long over;  // bytes the garbage rows of the last M-block may read past the end of a stage
   double cost;
   bool ok;
 };
 
+// measured (scripts/umma_rate.cu): clocks per M128 x N x K16 MMA = max(N/2, (4096 + 32 N) / 128) — SMEM operand fetch bound
+static inline double mma_clk(int n) { return std::max(n / 2.0, (4096.0 + 32.0 * n) / 128.0) + 4.0; }
+
 static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nmaps, int CoutPad, int ks, int mode,
-                            int num_sms, bool allow_split) {
-  const int halo = ks / 2, ntaps = ks * ks * ks;
+                            int num_sms, int max_split, int stat_gran) {
+  const int halo = ks / 2, KD = ks, KHW = ks * ks;
   const int Ktotal = chan_per_map * nmaps;
   IgemmPlan best; best.ok = false; best.cost = 1e30;
-  const int bn_top = (mode == 2) ? std::min(CoutPad / 8, 256) : (CoutPad <= 256 ? CoutPad : 256);
-  const int bn_cands[6] = {bn_top, 256, 128, 64, 32, 16};
   const int env_td = getenv("B3D_TD") ? atoi(getenv("B3D_TD")) : 0;
   const int env_th = getenv("B3D_TH") ? atoi(getenv("B3D_TH")) : 0;
+  const int env_tw = getenv("B3D_TW") ? atoi(getenv("B3D_TW")) : 0;
   const int env_kc = getenv("B3D_KC") ? atoi(getenv("B3D_KC")) : 0;
   const int env_bn = getenv("B3D_BN") ? atoi(getenv("B3D_BN")) : 0;
-  int TW = W;
-  if (W + 2 * halo > 256) TW = 128;
-  for (int TD = 1; TD <= 16 && TD <= D; TD *= 2)
-    for (int TH = 1; TH <= 64 && TH <= H; TH *= 2)
-      for (int KC = 64; KC >= 16; KC /= 2)
-        for (int bi = 0; bi < 6; ++bi) {
-          const int BN = bn_cands[bi];
-          if (bi > 0 && (BN >= bn_cands[0])) continue;
-          if (BN > 256 || BN % 16) continue;
-          if (mode == 2 && (BN > CoutPad / 8 || (CoutPad / 8) % BN)) continue;  // pixel shuffle: n-block inside one tap
-          if (chan_per_map % KC) continue;
+  const int bn_cands[5] = {256, 128, 64, 32, 16};
+  for (int patch = 1; patch >= 0; --patch) {
+    // patch mode: tile = TD x (16 a) x (8 b), M-block = 16 rows x 8 columns (no wasted M rows)
+    // linear mode: tile rows are TW wide (whole W when it fits), M-block = 128 consecutive halo-pitched positions
+    for (int TD = 1; TD <= 16 && TD <= std::max(D, 1); TD *= 2)
+      for (int TH = patch ? 16 : 1; TH <= 64; TH *= 2)
+        for (int TWi = 0; TWi < 6; ++TWi) {
+          int TW;
+          if (patch) { TW = 8 << TWi; if (TW > 128) continue; if (H < 16 || W < 8) continue; if (TW / 2 >= W && TWi > 0) continue; }
+          else { if (TWi > 0) continue; TW = (W + 2 * halo > 256) ? 128 : W; }
+          if (TH / 2 >= H && TH > (patch ? 16 : 1)) continue;
           if (env_td && TD != env_td) continue;
           if (env_th && TH != env_th) continue;
-          if (env_kc && KC != env_kc) continue;
-          if (env_bn && BN != env_bn) continue;
-          const int BD = TD + 2 * halo, BH = TH + 2 * halo, BW = TW + 2 * halo;
-          if (BD > 256 || BH > 256 || BW > 256) continue;
-          const long long box_vox = (long long)BD * BH * BW;
-          const long long RB = KC * 2;
-          const long long span = (long long)(TD - 1) * BH * BW + (long long)(TH - 1) * BW + TW;
-          const bool row_mode = (TW % 128 == 0);
-          const int MB = row_mode ? TD * TH * (TW / 128) : (int)((span + 127) / 128);
-          if (MB * BN > 512) continue;
-          const int acc_bufs = (2 * MB * BN <= 512) ? 2 : 1;
-          const long long a = (box_vox * RB + 1023) / 1024 * 1024, b = ((long long)ntaps * BN * RB + 1023) / 1024 * 1024;
-          const int k_chunks = Ktotal / KC;
-          int stages = (int)std::min<long long>(4, kSmemBudget / (a + b));
-          if (stages < 1) continue;
-          if (stages < 2) continue;
-          const long long maxoff = (row_mode ? span : (long long)MB * 128) + (long long)(ks - 1) * (BH * BW + BW + 1);
-          const long long over = std::max<long long>(0, maxoff - box_vox) * RB;
-          if (over > (long long)stages * b) continue;  // garbage rows must still read inside our smem
-          const int n_blocks = (CoutPad + BN - 1) / BN;
-          const long long tiles = (long long)N * ((D + TD - 1) / TD) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-          long long items = tiles * n_blocks;
-          int ksplit = 1;
-          if (allow_split && items < num_sms && k_chunks > 1) {
-            ksplit = (int)std::min<long long>(k_chunks, (num_sms + items - 1) / items);
-            const int cps = (k_chunks + ksplit - 1) / ksplit;
-            ksplit = (k_chunks + cps - 1) / cps;
+          if (env_tw && TW != env_tw) continue;
+          const int BH = TH + 2 * halo, BW = TW + 2 * halo;
+          if (BH > 256 || BW > 256 || TD > 256) continue;
+          const long long box_vox = (long long)TD * BH * BW;
+          int MB;
+          long long maxrow;  // one past the last box position any M-block row can touch (taps included)
+          if (patch) {
+            MB = TD * (TH / 16) * (TW / 8);
+            maxrow = box_vox;
+          } else {
+            const long long span = (long long)(TD - 1) * BH * BW + (long long)(TH - 1) * BW + TW;
+            MB = (int)((span + 127) / 128);
+            maxrow = (long long)MB * 128 + (long long)(ks - 1) * (BW + 1);
           }
-          const int cps = (k_chunks + ksplit - 1) / ksplit;
-          const double clk_per_mma = std::max(BN / 2.0, 32.0 + BN / 4.0);
-          const double mma_clk = (double)MB * ntaps * (KC / 16) * cps * clk_per_mma;
-          const double load_clk = (double)(a + b) * cps / 40.0;
-          const double epi_clk = (double)MB * (BN / 16) * 150.0;
-          double item_clk = std::max(mma_clk, load_clk);
-          item_clk = (acc_bufs == 2) ? std::max(item_clk, epi_clk) : item_clk + epi_clk;
-          const long long its = items * ksplit;
-          const long long waves = (its + num_sms - 1) / num_sms;
-          double cost = (double)waves * item_clk + 3000.0;
-          if (ksplit > 1) cost += 4000.0;
-          if (stages < 3) cost *= 1.05;
-          if (cost < best.cost) {
-            best.ok = true; best.cost = cost; best.TD = TD; best.TH = TH; best.TW = TW; best.KC = KC; best.BN = BN;
-            best.MB = MB; best.stages = stages; best.acc_bufs = acc_bufs; best.ksplit = ksplit;
-          }
+          if (MB > IG_MAXMB) continue;
+          for (int KC = 64; KC >= 16; KC /= 2)
+            for (int bi = 0; bi < 5; ++bi) {
+              const int BN = bn_cands[bi];
+              if (BN > CoutPad && BN != 16) continue;
+              if (BN > CoutPad) continue;
+              if (CoutPad % BN) continue;
+              if (mode == 2 && (BN > CoutPad / 8 || (CoutPad / 8) % BN)) continue;  // pixel shuffle: n-block inside one tap
+              if (chan_per_map % KC) continue;
+              if (env_kc && KC != env_kc) continue;
+              if (env_bn && BN != env_bn) continue;
+              if (stat_gran && BN / stat_gran > 16) continue;
+              if (MB * BN > 512) continue;
+              const int acc_bufs = (2 * MB * BN <= 512) ? 2 : 1;
+              const long long RB = KC * 2;
+              const long long a = (box_vox * RB + 1023) / 1024 * 1024, b = ((long long)KHW * BN * RB + 1023) / 1024 * 1024;
+              int stages = (int)std::min<long long>(IG_MAXSTAGES, kSmemBudget / (a + b));
+              if (stages < 2) continue;
+              const long long over = std::max<long long>(0, maxrow - box_vox) * RB;
+              if ((a + b) * stages + over > kSmemBudget) continue;  // garbage rows must still read inside our allocation
+              const int k_chunks = Ktotal / KC;
+              const int steps_total = k_chunks * KD;
+              const int n_blocks = CoutPad / BN;
+              const long long tiles = (long long)N * ((D + TD - 1) / TD) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+              const long long items = tiles * n_blocks;
+              int ksplit = 1;
+              if (max_split > 1 && items * 2 <= num_sms && steps_total > 1 && !getenv("B3D_NOSPLIT")) {
+                ksplit = (int)std::min<long long>(std::min(steps_total, max_split), num_sms / items);
+                const int sps = (steps_total + ksplit - 1) / ksplit;
+                ksplit = (steps_total + sps - 1) / sps;
+              }
+              const int sps = (steps_total + ksplit - 1) / ksplit;
+              const double mclk = (double)MB * KHW * (KC / 16) * sps * mma_clk(BN);
+              const double load_clk = (double)(a + b) * sps / 28.0;  // ~28 B/clk/SM of L2->SMEM when every SM streams
+              const double epi_clk = (double)MB * (BN / 16) * (ksplit > 1 ? 100.0 : 70.0) + 300.0;
+              double item_clk = std::max(mclk, load_clk);
+              item_clk = (acc_bufs == 2) ? std::max(item_clk, epi_clk) : item_clk + epi_clk;
+              const long long its = items * ksplit;
+              const long long waves = (its + num_sms - 1) / num_sms;
+              double cost = (double)waves * item_clk + 3000.0;
+              if (ksplit > 1) cost += 6000.0 + (double)N * D * H * W * CoutPad * 4.0 * (ksplit + 1) / (num_sms * 20.0);  // finalize pass
+              if (stages < 3) cost *= 1.15;
+              if (cost < best.cost) {
+                best.ok = true; best.cost = cost; best.TD = TD; best.TH = TH; best.TW = TW; best.KC = KC; best.BN = BN;
+                best.MB = MB; best.GS = patch ? BW : 8; best.stages = stages; best.acc_bufs = acc_bufs; best.ksplit = ksplit;
+                best.patch = patch; best.over = over;
+              }
+            }
         }
+  }
   return best;
 }
-
-static bool g_smem_attr_set = false;
 
 // Generic launcher.  `x_maps`: nmaps activation views (base pointer + dims + byte strides), each with `chan_per_map`
 // channels (multiple of 16).  Output space extent is (N,D,H,W).
@@ -473,22 +554,37 @@ struct ActView {
   int C;                     // channels addressable (multiple of 8)
 };
 
+template <int BN, int KC>
+static int ig_launch(const IgParams& P, size_t smem, int grid, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    B3D_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  igemm_kernel<BN, KC><<<grid, IG_THREADS, smem, stream>>>(P); ++g_b3d_launches;
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
 static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf16* wpack, int w_rows, int ks,
                      int N, int D, int H, int W, int Cout, int mode, bf16* out, long long ld_out, int ps_cout,
                      const float* bias, double* stats, int cpg, int stats_groups, int stats_batch, float* ws,
                      size_t ws_bytes, int* err_flag, cudaStream_t stream) {
-  const int ntaps = ks * ks * ks, halo = ks / 2;
+  const int halo = ks / 2, KD = ks, KHW = ks * ks;
   const int num_sms = b3d_num_sms();
   const int CoutPad = w_rows;  // rows in the packed weight tensor (multiple of 16)
   B3D_REQUIRE(chan_per_map % 16 == 0, "igemm: channels per K-map (%d) must be a multiple of 16", chan_per_map);
   B3D_REQUIRE(CoutPad % 16 == 0, "igemm: packed weight rows (%d) must be a multiple of 16", CoutPad);
   B3D_REQUIRE(nmaps >= 1 && nmaps <= 8, "igemm: nmaps out of range");
+  int stat_gran = 0;
   if (stats) {
     B3D_REQUIRE(cpg == 1 || cpg == 2 || cpg == 4 || cpg == 8 || cpg % 16 == 0,
                 "igemm: channels-per-group %d unsupported (need 1,2,4,8 or a multiple of 16)", cpg);
+    stat_gran = cpg >= 16 ? 16 : (cpg >= 4 ? 4 : 1);
   }
-  const bool allow_split = (mode == 0) && ws != nullptr;
-  IgemmPlan pl = plan_igemm(N, D, H, W, chan_per_map, nmaps, CoutPad, ks, mode, num_sms, allow_split);
+  int max_split = 1;  // split-K partials are plain stores into per-split workspace slices [ksplit][V][Cout] fp32
+  if (mode == 0 && ws != nullptr && Cout % 8 == 0) max_split = (int)std::min<size_t>(64, ws_bytes / ((size_t)N * D * H * W * Cout * 4));
+  IgemmPlan pl = plan_igemm(N, D, H, W, chan_per_map, nmaps, CoutPad, ks, mode, num_sms, max_split, stat_gran);
   if (!pl.ok) {
     b3d_set_error("igemm: no tile plan for N=%d D=%d H=%d W=%d K=%dx%d Cout=%d ks=%d", N, D, H, W, nmaps, chan_per_map,
                   CoutPad, ks);
@@ -496,26 +592,36 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   }
   if (stats) B3D_REQUIRE(pl.BN / cpg <= 32 && (pl.BN % cpg == 0 || cpg % pl.BN == 0), "igemm: BN %d / cpg %d unsupported", pl.BN, cpg);
 
-  IgemmParams P;
+  IgParams P;
   memset(&P, 0, sizeof(P));
-  P.N = N; P.D = D; P.H = H; P.W = W; P.Cout = Cout; P.halo = halo; P.ks = ks;
+  P.N = N; P.D = D; P.H = H; P.W = W; P.Cout = Cout; P.halo = halo; P.ks = ks; P.KD = KD;
   P.TD = pl.TD; P.TH = pl.TH; P.TW = pl.TW;
-  P.BD = pl.TD + 2 * halo; P.BH = pl.TH + 2 * halo; P.BW = pl.TW + 2 * halo;
-  P.box_vox = P.BD * P.BH * P.BW;
-  P.row_mode = (pl.TW % 128 == 0) ? 1 : 0; P.xblocks = pl.TW / 128;
-  P.MB = pl.MB; P.BN = pl.BN; P.n_blocks = (CoutPad + pl.BN - 1) / pl.BN; P.KC = pl.KC;
-  P.chunks_per_map = chan_per_map / pl.KC; P.k_chunks = P.chunks_per_map * nmaps;
-  P.stages = pl.stages; P.acc_bufs = pl.acc_bufs; P.acc_stride = pl.MB * pl.BN;
+  P.BH = pl.TH + 2 * halo; P.BW = pl.TW + 2 * halo;
+  P.MB = pl.MB; P.GS = pl.GS;
+  if (pl.patch) {
+    int m = 0;
+    for (int pz = 0; pz < P.TD; ++pz)
+      for (int pa = 0; pa < P.TH / 16; ++pa)
+        for (int pb = 0; pb < P.TW / 8; ++pb) P.mb_base[m++] = (pz * P.BH + pa * 16) * P.BW + pb * 8;
+  } else {
+    for (int m = 0; m < P.MB; ++m) P.mb_base[m] = m * 128;
+  }
+  const int BN = pl.BN, KC = pl.KC, RB = KC * 2;
+  P.n_blocks = CoutPad / BN;
+  P.chunks_per_map = chan_per_map / KC; P.k_chunks = P.chunks_per_map * nmaps;
+  P.stages = pl.stages; P.acc_bufs = pl.acc_bufs; P.acc_stride = pl.MB * BN;
   int cols = P.acc_bufs * P.acc_stride, tc = 32;
   while (tc < cols) tc *= 2;
   P.tmem_cols = tc;
   P.tiles_x = (W + P.TW - 1) / P.TW; P.tiles_y = (H + P.TH - 1) / P.TH; P.tiles_z = (D + P.TD - 1) / P.TD;
   P.num_tiles = N * P.tiles_x * P.tiles_y * P.tiles_z;
-  P.ksplit = pl.ksplit; P.chunks_per_split = (P.k_chunks + pl.ksplit - 1) / pl.ksplit;
+  P.steps_total = P.k_chunks * KD;
+  P.ksplit = pl.ksplit; P.steps_per_split = (P.steps_total + pl.ksplit - 1) / pl.ksplit;
   P.num_items = P.num_tiles * P.n_blocks * P.ksplit;
-  P.RB = P.KC * 2; P.layout_type = (P.RB == 128) ? 2 : (P.RB == 64 ? 4 : 6);
-  P.a_tx_bytes = (uint32_t)P.box_vox * P.RB; P.b_tx_bytes = (uint32_t)ntaps * P.BN * P.RB;
-  P.a_stage_bytes = (P.a_tx_bytes + 1023u) / 1024u * 1024u; P.b_stage_bytes = (P.b_tx_bytes + 1023u) / 1024u * 1024u;
+  const long long box_vox = (long long)P.TD * P.BH * P.BW;
+  P.a_tx = (uint32_t)(box_vox * RB); P.w_tx = (uint32_t)(KHW * BN * RB);
+  P.w_off = (P.a_tx + 1023u) / 1024u * 1024u;
+  P.stage_bytes = P.w_off + (P.w_tx + 1023u) / 1024u * 1024u;
   P.mode = mode; P.out = out; P.ld_out = ld_out; P.ps_cout = ps_cout; P.bias = bias;
   P.stats = stats; P.cpg = cpg > 0 ? cpg : 16; P.stats_groups = stats_groups; P.stats_batch = stats_batch;
   P.err = err_flag;
@@ -523,50 +629,50 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   const bool split = P.ksplit > 1;
   const long long V = (long long)N * D * H * W;
   if (split) {
-    B3D_REQUIRE(ws_bytes >= (size_t)V * Cout * 4, "igemm: split-K workspace too small (%zu < %lld)", ws_bytes,
-                V * Cout * 4);
-    B3D_REQUIRE(Cout % 8 == 0, "igemm: split-K needs Cout %% 8 == 0");
-    B3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)V * Cout * 4, stream));
-    P.mode = 1; P.out_f32 = ws; P.ld_f32 = Cout; P.stats = nullptr; P.bias = nullptr;
+    P.mode = 1; P.out_f32 = ws; P.ld_f32 = Cout; P.slice_f32 = V * Cout; P.stats = nullptr; P.bias = nullptr;
   }
 
   for (int m = 0; m < nmaps; ++m) {
     const ActView& v = views[m];
     uint64_t dims[5] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.D, (uint64_t)v.N};
     uint64_t strides[4] = {(uint64_t)v.sW, (uint64_t)v.sH, (uint64_t)v.sD, (uint64_t)v.sN};
-    uint32_t box[5] = {(uint32_t)P.KC, (uint32_t)P.BW, (uint32_t)P.BH, (uint32_t)P.BD, 1};
-    int rc = b3d_encode_tmap_bf16(&P.tmA[m], v.base, 5, dims, strides, box, P.RB);
+    uint32_t box[5] = {(uint32_t)KC, (uint32_t)P.BW, (uint32_t)P.BH, (uint32_t)P.TD, 1};
+    int rc = b3d_encode_tmap_bf16(&P.tmA[m], v.base, 5, dims, strides, box, RB);
     if (rc) return rc;
   }
   {
+    // packed weights [(kh,kw)][kd][rows][Kp] (kd fastest of the taps): a pipeline step takes the KHW taps of one kd
     const int Kp = chan_per_map * nmaps;
-    uint64_t dims[3] = {(uint64_t)Kp, (uint64_t)CoutPad, (uint64_t)ntaps};
-    uint64_t strides[2] = {(uint64_t)Kp * 2, (uint64_t)CoutPad * Kp * 2};
-    uint32_t box[3] = {(uint32_t)P.KC, (uint32_t)P.BN, (uint32_t)ntaps};
-    int rc = b3d_encode_tmap_bf16(&P.tmW, wpack, 3, dims, strides, box, P.RB);
+    uint64_t dims[4] = {(uint64_t)Kp, (uint64_t)CoutPad, (uint64_t)KD, (uint64_t)KHW};
+    uint64_t strides[3] = {(uint64_t)Kp * 2, (uint64_t)CoutPad * Kp * 2, (uint64_t)KD * CoutPad * Kp * 2};
+    uint32_t box[4] = {(uint32_t)KC, (uint32_t)BN, 1, (uint32_t)KHW};
+    int rc = b3d_encode_tmap_bf16(&P.tmW, wpack, 4, dims, strides, box, RB);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 16 * P.stages + 48 + 64 * 4 + 128 + 1024;
-  if (!g_smem_attr_set) {
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    g_smem_attr_set = true;
-  }
+  const size_t smem = (size_t)P.stages * P.stage_bytes + std::max<size_t>((size_t)pl.over, 16 * IG_MAXSTAGES + 48 + 64 * 4 + 128) + 1024;
   B3D_REQUIRE(smem <= 227 * 1024, "igemm: smem %zu too large", smem);
   const int grid = std::min(P.num_items, num_sms);
   if (getenv("B3D_VERBOSE"))
     fprintf(stderr,
-            "[b3d] igemm N%d D%d H%d W%d K=%dx%d Cout=%d(ks%d mode%d) tile %dx%dx%d KC%d BN%d MB%d stages%d acc%d "
+            "[b3d] igemm N%d D%d H%d W%d K=%dx%d Cout=%d(ks%d mode%d) tile %dx%dx%d %s KC%d BN%d MB%d stages%d acc%d "
             "split%d items%d smem%zu tmem%d\n",
-            N, D, H, W, nmaps, chan_per_map, Cout, ks, mode, P.TD, P.TH, P.TW, P.KC, P.BN, P.MB, P.stages, P.acc_bufs,
-            P.ksplit, P.num_items, smem, P.tmem_cols);
-  igemm_kernel<<<grid, IGEMM_THREADS, smem, stream>>>(P); ++g_b3d_launches;
-  B3D_CHECK_CUDA(cudaGetLastError());
+            N, D, H, W, nmaps, chan_per_map, Cout, ks, mode, P.TD, P.TH, P.TW, pl.patch ? "patch" : "linear", KC, BN, P.MB,
+            P.stages, P.acc_bufs, P.ksplit, P.num_items, smem, P.tmem_cols);
+  int rc = B3D_ERR_UNSUPPORTED;
+#define IG_CASE(B, K) if (BN == B && KC == K) rc = ig_launch<B, K>(P, smem, grid, stream);
+  IG_CASE(16, 16) IG_CASE(16, 32) IG_CASE(16, 64)
+  IG_CASE(32, 16) IG_CASE(32, 32) IG_CASE(32, 64)
+  IG_CASE(64, 16) IG_CASE(64, 32) IG_CASE(64, 64)
+  IG_CASE(128, 16) IG_CASE(128, 32) IG_CASE(128, 64)
+  IG_CASE(256, 16) IG_CASE(256, 32) IG_CASE(256, 64)
+#undef IG_CASE
+  if (rc) return rc;
   if (split) {
     const int chunks = Cout / 8;
     const long long total = V * chunks;
     int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms * 8);
     // keep each block inside as few samples as possible
-    igemm_finalize_kernel<<<blocks, 256, 0, stream>>>(ws, V, Cout, (long long)D * H * W, bias, out, ld_out, stats,
+    igemm_finalize_kernel<<<blocks, 256, 0, stream>>>(ws, P.ksplit, V, Cout, (long long)D * H * W, bias, out, ld_out, stats,
                                                       cpg > 0 ? cpg : 16, stats_groups, stats_batch); ++g_b3d_launches;
     B3D_CHECK_CUDA(cudaGetLastError());
   }

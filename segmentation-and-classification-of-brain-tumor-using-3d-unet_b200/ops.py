@@ -21,8 +21,8 @@ PROFILE = None  # bench.py sets this to a list: (family, algorithmic flops, star
 
 
 class _prof:
-    def __init__(self, family, flops):
-        self.family, self.flops = family, flops
+    def __init__(self, family, flops, tag=""):
+        self.family, self.flops, self.tag = family, flops, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -34,7 +34,7 @@ class _prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.b.record()
-            PROFILE.append((self.family, self.flops, self.a, self.b))
+            PROFILE.append((self.family, self.flops, self.a, self.b, self.tag))
         return False
 
 
@@ -107,9 +107,11 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
     stats = None
     if groups:
         stats = torch.zeros((1 if stats_batch else n, groups, 2), dtype=torch.float64, device=dev)
-    ws_bytes = n * d * h * w * cout * 4
-    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes <= (1 << 28) else None
-    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * ks ** 3):
+    # split-K workspace: up to 16 fp32 partial slices [split][V][Cout]; only small (deep-level) problems ever split
+    one = n * d * h * w * cout * 4
+    ws_bytes = one * 16 if one * 16 <= (1 << 26) else 0
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * ks ** 3, "conv%d %dx%dx%dx%d %d->%d" % (ks, n, d, h, w, cin, cout)):
         check(_L().b3d_conv_fprop(ptr(x), c_ll(ld(x)), ptr(wpack), c_int(w_rows), ptr(bias), ptr(out), c_ll(ld(out)),
                                   c_int(n), c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), c_int(ks), ptr(stats),
                                   c_int(groups), c_int(1 if stats_batch else 0), ptr(ws),
@@ -121,7 +123,7 @@ def convT2_fprop(x, wpack, bias, cout, out=None):
     n, d, h, w, cin = x.shape
     if out is None:
         out = new_act(n, 2 * d, 2 * h, 2 * w, cout, x.device)
-    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * 8):
+    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * 8, "convT %dx%dx%dx%d %d->%d" % (n, d, h, w, cin, cout)):
         check(_L().b3d_convT2_fprop(ptr(x), c_ll(ld(x)), ptr(wpack), ptr(bias), ptr(out), c_ll(ld(out)), c_int(n), c_int(d),
                                     c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(_lib.err_flag(x.device)), stream_ptr()))
     return out
@@ -133,8 +135,9 @@ def convT2_dgrad(dy, wpack, w_rows, cin, out=None):
     dev = dy.device
     if out is None:
         out = new_act(n, d, h, w, cin, dev)
-    ws = torch.empty(n * d * h * w * cin, dtype=torch.float32, device=dev)
-    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * 8):
+    one = n * d * h * w * cin
+    ws = torch.empty(one * 16 if one * 64 <= (1 << 26) else one, dtype=torch.float32, device=dev)
+    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * 8, "convT_dgrad %dx%dx%dx%d %d<-%d" % (n, d, h, w, cin, cout)):
         check(_L().b3d_convT2_dgrad(ptr(dy), c_ll(ld(dy)), ptr(wpack), c_int(w_rows), ptr(out), c_ll(ld(out)), c_int(n),
                                     c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(ws), c_sz(ws.numel() * 4),
                                     ptr(_lib.err_flag(dev)), stream_ptr()))
@@ -152,7 +155,7 @@ def conv_wgrad(x, dy, cin_real, cout, ks, dw=None, accumulate=False):
     cout_pad = roundup(cout, 16)
     assert dy.shape[-1] == cout and (cout_pad == cout or ld(dy) >= cout_pad), "dy must expose padded channels"
     ws = torch.empty(ks ** 3 * cin * cout_pad, dtype=torch.float32, device=dev)
-    with _prof("wgrad", 2.0 * n * d * h * w * cin_real * cout * ks ** 3):
+    with _prof("wgrad", 2.0 * n * d * h * w * cin_real * cout * ks ** 3, "wgrad%d %dx%dx%dx%d %d,%d" % (ks, n, d, h, w, cin, cout)):
         check(_L().b3d_conv_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
                                   c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cin_real), c_int(cout), c_int(ks), ptr(ws),
                                   c_sz(ws.numel() * 4), ptr(_lib.err_flag(dev)), stream_ptr()))
@@ -167,7 +170,7 @@ def convT2_wgrad(x, dy, cin, cout, dw=None, accumulate=False):
         dw = torch.empty((cin, cout, 2, 2, 2), dtype=torch.float32, device=dev)
         accumulate = False
     ws = torch.empty(8 * cin * cout, dtype=torch.float32, device=dev)
-    with _prof("wgrad", 2.0 * n * d * h * w * cin * cout * 8):
+    with _prof("wgrad", 2.0 * n * d * h * w * cin * cout * 8, "wgradT %dx%dx%dx%d %d,%d" % (n, d, h, w, cin, cout)):
         check(_L().b3d_convT2_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
                                     c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(ws), c_sz(ws.numel() * 4),
                                     ptr(_lib.err_flag(dev)), stream_ptr()))
