@@ -9,3 +9,6 @@
 int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
                    int N, int D, int H, int W, int Cin, int Cout, double* stats, int cpg, int stats_groups,
                    int stats_batch, int* err_flag, cudaStream_t stream);
+// conv_wg2.cu: 3x3x3 weight gradient with swizzled MN-major operands (W a multiple of 16).  Same return convention.
+int b3d_try_wg2(const void* x, long long ldx, int Cin, const void* dy, long long lddy, int Cout_pad, int N, int D, int H, int W,
+                float* dwacc, int Cin_pad, int* err_flag, cudaStream_t stream);

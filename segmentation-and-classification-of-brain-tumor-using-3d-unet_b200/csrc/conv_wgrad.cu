@@ -492,7 +492,11 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   }
   YView yv;
   yv.base = dy; yv.sW = lddy * 2; yv.sH = yv.sW * w; yv.sND = yv.sH * h;
-  int rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
+  int rc = 1;
+  if (ks == 3 && Cin % 16 == 0)  // swizzled MN-major kernel (conv_wg2.cu) when the rows are a multiple of 16 wide
+    rc = b3d_try_wg2(x, ldx, Cin, dy, lddy, Cout_pad, N, D, H, W, ws, Cin, err_flag, st);
+  if (rc < 0) return rc;
+  if (rc > 0) rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
   const long long total = (long long)ntaps * Cin_real * Cout;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
