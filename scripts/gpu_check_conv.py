@@ -139,6 +139,10 @@ if __name__ == "__main__":
         allok &= conv_case(2, 2, 16, 16, 16, 64, 3)
     if which == "one":  # a single launch of the dominant layer shape, for ncu
         allok &= conv_case(2, 128, 128, 128, 32, 32, 3)
+    if which == "pw":
+        allok &= conv_case(2, 128, 128, 128, 16, 32, 1, iters=5)
+    if which == "pw64":
+        allok &= conv_case(2, 128, 128, 128, 64, 32, 1, iters=5)
     if which == "l2":
         allok &= conv_case(2, 32, 32, 32, 128, 128, 3, iters=5)
     if which == "l3":

@@ -27,6 +27,7 @@
 #include "b3d_internal.h"
 #include <algorithm>
 #include <math.h>
+#include <type_traits>
 
 #define IG_THREADS 192
 #define IG_MAXMB 32
@@ -240,81 +241,114 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       mbar_wait(tfull0 + 8 * a, aph, P.err, 4);
       tc_fence_after();
       const int cmax = (P.mode == 2 ? P.ps_cout : P.Cout);
-      for (int mb = 0; mb < P.MB; ++mb) {
-        const int p = P.mb_base[mb] + (row >> 3) * P.GS + (row & 7);
-        const int pz = p / plane, pr = p - pz * plane;
-        const int py = pr / P.BW, px = pr - py * P.BW;
-        const int z = tz * P.TD + pz, y = ty * P.TH + py, x = tx * P.TW + px;
-        const bool valid = (pz < P.TD) && (py < P.TH) && (px < P.TW) && (z < P.D) && (y < P.H) && (x < P.W);
-        long long vox;
-        int ch_base;
-        if (P.mode == 2) {
-          const int t8 = n0 / P.ps_cout;
-          ch_base = n0 - t8 * P.ps_cout;
-          const int oz = 2 * z + (t8 >> 2), oy = 2 * y + ((t8 >> 1) & 1), ox = 2 * x + (t8 & 1);
-          vox = (((long long)n * (2 * P.D) + oz) * (2 * P.H) + oy) * (2 * P.W) + ox;
-        } else {
-          ch_base = n0;
-          vox = (((long long)n * P.D + z) * P.H + y) * P.W + x;
-        }
-        const uint32_t trow = tmem_base + a * P.acc_stride + mb * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-        for (int j0 = 0; j0 < BN; j0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(trow + j0, r);
-          tmem_ld_wait();
-          float v[16];
-          const int c0 = ch_base + j0;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f = __uint_as_float(r[j]);
-            if (P.bias != nullptr && c0 + j < cmax) f += __ldg(P.bias + c0 + j);
-            v[j] = f;
+      int t8 = 0, ch_base = n0;
+      if (P.mode == 2) { t8 = n0 / P.ps_cout; ch_base = n0 - t8 * P.ps_cout; }
+      const bool full = (ch_base + BN <= cmax);   // every column of this n-block is a real channel
+      // specialised bodies: one (mode, statistics granule) combination runs, without per-element predicates
+      auto body = [&](auto MODE_c, auto GRAN_c, auto FULL_c) {
+        constexpr int MODE = decltype(MODE_c)::value, GRAN = decltype(GRAN_c)::value;
+        constexpr bool FULL = decltype(FULL_c)::value;
+        for (int mb = 0; mb < P.MB; ++mb) {
+          const int p = P.mb_base[mb] + (row >> 3) * P.GS + (row & 7);
+          const int pz = p / plane, pr = p - pz * plane;
+          const int py = pr / P.BW, px = pr - py * P.BW;
+          const int z = tz * P.TD + pz, y = ty * P.TH + py, x = tx * P.TW + px;
+          const bool valid = (pz < P.TD) && (py < P.TH) && (px < P.TW) && (z < P.D) && (y < P.H) && (x < P.W);
+          long long vox;
+          if (MODE == 2) {
+            const int oz = 2 * z + (t8 >> 2), oy = 2 * y + ((t8 >> 1) & 1), ox = 2 * x + (t8 & 1);
+            vox = (((long long)n * (2 * P.D) + oz) * (2 * P.H) + oy) * (2 * P.W) + ox;
+          } else {
+            vox = (((long long)n * P.D + z) * P.H + y) * P.W + x;
           }
-          if (valid) {
-            if (P.stats != nullptr) {
-              if (gran == 16) {
-                float s1 = 0.f, s2 = 0.f;
+          const uint32_t trow = tmem_base + a * P.acc_stride + mb * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { s1 += v[j]; s2 += v[j] * v[j]; }
-                a1[j0 / 16] += s1; a2[j0 / 16] += s2;
-              } else if (gran == 4) {
+          for (int j0 = 0; j0 < BN; j0 += 32) {
+            constexpr int NC = (BN >= 32) ? 32 : 16;   // columns per TMEM round trip
+            uint32_t r[NC];
+            tmem_ld16(trow + j0, r);
+            if (NC == 32) tmem_ld16(trow + j0 + 16, r + 16);
+            tmem_ld_wait();
+            float v[NC];
+            const int c0 = ch_base + j0;
+#pragma unroll
+            for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+            if (P.bias != nullptr) {
+              if (FULL) {
+#pragma unroll
+                for (int j = 0; j < NC; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + c0 + j));
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) if (c0 + j < cmax) v[j] += __ldg(P.bias + c0 + j);
+              }
+            }
+            if (valid) {
+              if (GRAN == 16) {
+#pragma unroll
+                for (int h = 0; h < NC / 16; ++h) {
+                  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { s1 += v[16 * h + j]; s2 = fmaf(v[16 * h + j], v[16 * h + j], s2); }
+                  a1[(j0 / 16 + h) & 15] += s1; a2[(j0 / 16 + h) & 15] += s2;
+                }
+              } else if (GRAN == 4) {
                 if (j0 < 64) {
 #pragma unroll
-                  for (int qd = 0; qd < 4; ++qd) {
+                  for (int qd = 0; qd < NC / 4; ++qd) {
                     const int ai = (j0 / 4 + qd) & 15;
                     a1[ai] += (v[4 * qd] + v[4 * qd + 1]) + (v[4 * qd + 2] + v[4 * qd + 3]);
                     a2[ai] += (v[4 * qd] * v[4 * qd] + v[4 * qd + 1] * v[4 * qd + 1]) +
                               (v[4 * qd + 2] * v[4 * qd + 2] + v[4 * qd + 3] * v[4 * qd + 3]);
                   }
                 }
-              } else if (j0 == 0) {
+              } else if (GRAN == 1) {
+                if (j0 == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { a1[j] += v[j]; a2[j] += v[j] * v[j]; }
+                  for (int j = 0; j < 16; ++j) { a1[j] += v[j]; a2[j] = fmaf(v[j], v[j], a2[j]); }
+                }
               }
-            }
-            if (P.mode == 1) {
-              float* o = P.out_f32 + split * P.slice_f32 + vox * P.ld_f32 + c0;
-              if (c0 + 16 <= cmax) {
-                const uint4* pv = reinterpret_cast<const uint4*>(v);
-                stg32(o, pv[0], pv[1]);
-                stg32(o + 8, pv[2], pv[3]);
+              if (MODE == 1) {
+                float* o = P.out_f32 + split * P.slice_f32 + vox * P.ld_f32 + c0;
+                if (FULL) {
+                  const uint4* pv = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+                  for (int h = 0; h < NC / 8; ++h) stg32(o + 8 * h, pv[2 * h], pv[2 * h + 1]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < NC; ++j) if (c0 + j < cmax) o[j] = v[j];
+                }
               } else {
+                bf16* o = P.out + vox * P.ld_out + c0;
+                if (FULL && ((reinterpret_cast<uintptr_t>(o) & 31) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (c0 + j < cmax) o[j] = v[j];
-              }
-            } else {
-              bf16* o = P.out + vox * P.ld_out + c0;
-              if (c0 + 16 <= cmax && ((reinterpret_cast<uintptr_t>(o) & 31) == 0)) stg32(o, pack8(v), pack8(v + 8));
-              else {
-                if (c0 + 8 <= cmax) stg16(o, pack8(v));
-                if (c0 + 16 <= cmax) stg16(o + 8, pack8(v + 8));
+                  for (int h = 0; h < NC / 16; ++h) stg32(o + 16 * h, pack8(v + 16 * h), pack8(v + 16 * h + 8));
+                } else {
+#pragma unroll
+                  for (int h = 0; h < NC / 8; ++h) if (c0 + 8 * h + 8 <= cmax) stg16(o + 8 * h, pack8(v + 8 * h));
+                }
               }
             }
           }
         }
-      }
+      };
+      using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+      using I4 = std::integral_constant<int, 4>; using I16 = std::integral_constant<int, 16>;
+      if (!full) {
+        if (P.mode == 1) body(I1{}, I0{}, std::false_type{});
+        else if (P.mode == 2) body(I2{}, I0{}, std::false_type{});
+        else if (P.stats == nullptr) body(I0{}, I0{}, std::false_type{});
+        else if (gran == 16) body(I0{}, I16{}, std::false_type{});
+        else if (gran == 4) body(I0{}, I4{}, std::false_type{});
+        else body(I0{}, I1{}, std::false_type{});
+      } else if (P.mode == 1) body(I1{}, I0{}, std::true_type{});
+      else if (P.mode == 2) body(I2{}, I0{}, std::true_type{});
+      else if (P.stats == nullptr) body(I0{}, I0{}, std::true_type{});
+      else if (gran == 16) body(I0{}, I16{}, std::true_type{});
+      else if (gran == 4) body(I0{}, I4{}, std::true_type{});
+      else body(I0{}, I1{}, std::true_type{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * a);
@@ -466,7 +500,7 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
   const int env_kc = getenv("B3D_KC") ? atoi(getenv("B3D_KC")) : 0;
   const int env_bn = getenv("B3D_BN") ? atoi(getenv("B3D_BN")) : 0;
   const int bn_cands[5] = {256, 128, 64, 32, 16};
-  for (int patch = 1; patch >= 0; --patch) {
+  for (int patch = getenv("B3D_NOPATCH") ? 0 : 1; patch >= 0; --patch) {
     // patch mode: tile = TD x (16 a) x (8 b), M-block = 16 rows x 8 columns (no wasted M rows)
     // linear mode: tile rows are TW wide (whole W when it fits), M-block = 128 consecutive halo-pitched positions
     for (int TD = 1; TD <= 16 && TD <= std::max(D, 1); TD *= 2)

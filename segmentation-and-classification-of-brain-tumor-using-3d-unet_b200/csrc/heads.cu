@@ -82,6 +82,11 @@ __global__ void __launch_bounds__(256) ds_head_bwd_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) gw[k][j] = 0.f;
   float gb[KCLS] = {0.f, 0.f, 0.f, 0.f};
+  float wr[KCLS][8];  // this lane's weights (its channel chunk is fixed when nchunks == 1): no bank-conflicted LDS in the loop
+#pragma unroll
+  for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[k][j] = (lc < C8) ? sw[k * C + lc * 8 + j] : 0.f;
   for (long long v0 = warp_id * vpw; v0 < NV; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     if (v >= NV) continue;
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(256) ds_head_bwd_kernel(const float* __restric
       for (int j = 0; j < 8; ++j) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < KCLS; ++k) s = fmaf(g[k], sw[k * C + c8 * 8 + j], s);
+        for (int k = 0; k < KCLS; ++k) s = fmaf(g[k], (nchunks == 1) ? wr[k][j] : sw[k * C + c8 * 8 + j], s);
         o[j] = ACC ? o[j] + s : s;
       }
       stg16(dx + v * lddx + c8 * 8, pack8(o));

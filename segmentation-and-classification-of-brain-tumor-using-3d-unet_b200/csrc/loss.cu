@@ -227,6 +227,130 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
   }
 }
 
+
+// backward, 4 voxels (consecutive x) per thread: the 7-point boundary stencil is served by 128-bit loads (W % 4 == 0)
+__device__ __forceinline__ float sgnf(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(256) loss_bwd_vec4_kernel(const float* __restrict__ prob, const float* __restrict__ E,
+                                                            const long long* __restrict__ target, const double* __restrict__ acc,
+                                                            const float* __restrict__ gscale, float wscale,
+                                                            float* __restrict__ dlogits, int N, int D, int H, int W, LossCfg cfg) {
+  __shared__ float s_d1[KC], s_d2[KC], s_t1[KC], s_t2[KC], s_t3[KC];
+  const long long V = (long long)D * H * W;
+  const int n = blockIdx.y;
+  if (threadIdx.x < KC) {
+    const double* a = acc + (long long)n * ACC_STRIDE;
+    const int c = threadIdx.x;
+    const double I = a[c], P = a[4 + c], T = a[8 + c];
+    const double U = P + T + cfg.smooth;
+    s_d1[c] = (float)(-(2.0 / U) / (N * KC));
+    s_d2[c] = (float)(((2.0 * I + cfg.smooth) / (U * U)) / (N * KC));
+    const double Dn = (1.0 - cfg.tv_alpha - cfg.tv_beta) * I + cfg.tv_alpha * P + cfg.tv_beta * T + cfg.tv_smooth;
+    s_t1[c] = (float)(-(1.0 / Dn) / (N * KC));
+    s_t2[c] = (float)(((I + cfg.tv_smooth) * (1.0 - cfg.tv_alpha - cfg.tv_beta) / (Dn * Dn)) / (N * KC));
+    s_t3[c] = (float)(((I + cfg.tv_smooth) * cfg.tv_alpha / (Dn * Dn)) / (N * KC));
+  }
+  __syncthreads();
+  const float g = gscale ? gscale[0] * wscale : wscale;
+  const float inv_nv = 1.f / ((float)N * (float)V);
+  const float wb = cfg.w_boundary * 2.f * inv_nv / KC;
+  const float* pn = prob + (long long)n * KC * V;
+  const float* En = E ? E + (long long)n * KC * V : nullptr;
+  const long long* tn = target + (long long)n * V;
+  float* dn = dlogits + (long long)n * KC * V;
+  const bool use_b = (cfg.w_boundary != 0.f) && En != nullptr;
+  const long long HW = (long long)H * W;
+  const long long V4 = V / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < V4; q += (long long)gridDim.x * blockDim.x) {
+    const long long v = q * 4;
+    const int x0 = (int)(v % W);
+    const int y = (int)((v / W) % H);
+    const int z = (int)(v / HW);
+    const longlong2 ta = __ldg(reinterpret_cast<const longlong2*>(tn + v));
+    const longlong2 tb = __ldg(reinterpret_cast<const longlong2*>(tn + v + 2));
+    const int t[4] = {(int)ta.x, (int)ta.y, (int)tb.x, (int)tb.y};
+    float p[KC][4], G[KC][4];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      const float4 pc = ld4(pn + c * V + v);
+      p[c][0] = pc.x; p[c][1] = pc.y; p[c][2] = pc.z; p[c][3] = pc.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float o = (c == t[i]) ? 1.f : 0.f;
+        G[c][i] = cfg.w_dice * (o * s_d1[c] + s_d2[c]) + cfg.w_tv * (o * (s_t1[c] + s_t2[c]) + s_t3[c]);
+      }
+    }
+    if (use_b) {
+      const bool hzp = z + 1 < D, hzm = z > 0, hyp = y + 1 < H, hym = y > 0, hxp = x0 + 4 < W, hxm = x0 > 0;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        const float* pc = pn + c * V + v;
+        const float* ec = En + c * V + v;
+        const float4 e4 = ld4(ec);
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        float gb[4] = {0.f, 0.f, 0.f, 0.f};
+        // z and y axes: whole-vector neighbours
+        if (hzp) { const float4 q4 = ld4(pc + HW); const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gb[i] -= sgnf(qv[i] - p[c][i]) * ev[i]; }
+        if (hzm) { const float4 q4 = ld4(pc - HW); const float4 f4 = ld4(ec - HW);
+          const float qv[4] = {q4.x, q4.y, q4.z, q4.w}; const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gb[i] += sgnf(p[c][i] - qv[i]) * fv[i]; }
+        if (hyp) { const float4 q4 = ld4(pc + W); const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gb[i] -= sgnf(qv[i] - p[c][i]) * ev[i]; }
+        if (hym) { const float4 q4 = ld4(pc - W); const float4 f4 = ld4(ec - W);
+          const float qv[4] = {q4.x, q4.y, q4.z, q4.w}; const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gb[i] += sgnf(p[c][i] - qv[i]) * fv[i]; }
+        // x axis: neighbours inside the vector, plus one scalar on each side
+        const float pxp = hxp ? __ldg(pc + 4) : 0.f;
+        const float pxm = hxm ? __ldg(pc - 1) : 0.f;
+        const float exm = hxm ? __ldg(ec - 1) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < 3 || hxp) { const float nb = (i < 3) ? p[c][i < 3 ? i + 1 : 3] : pxp; gb[i] -= sgnf(nb - p[c][i]) * ev[i]; }
+          if (i > 0 || hxm) { const float nb = (i > 0) ? p[c][i > 0 ? i - 1 : 0] : pxm; const float en = (i > 0) ? ev[i > 0 ? i - 1 : 0] : exm;
+            gb[i] += sgnf(p[c][i] - nb) * en; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) G[c][i] = fmaf(wb, gb[i], G[c][i]);
+      }
+    }
+    float out[KC][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) dot = fmaf(G[c][i], p[c][i], dot);
+      float ptv = p[0][i];
+#pragma unroll
+      for (int c = 1; c < KC; ++c) ptv = (t[i] == c || (c == KC - 1 && t[i] >= KC)) ? p[c][i] : ptv;
+      const float pt = fmaxf(ptv, 1e-38f);
+      const float ce = -logf(pt);
+      const float om = 1.f - pt;
+      float fprime = 0.f;
+      if (cfg.w_focal != 0.f) {
+        const float gm = cfg.f_gamma;
+        const float t1 = focal_pow(om, gm);
+        const float t2 = (gm == 0.f) ? 0.f : gm * focal_pow(om, gm - 1.f) * pt * ce;
+        fprime = cfg.w_focal * cfg.f_alpha * (t1 + t2) * inv_nv;
+      }
+      const float lin = fprime + cfg.w_ce * inv_nv;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        const float o = (c == t[i]) ? 1.f : 0.f;
+        out[c][i] = g * (p[c][i] * (G[c][i] - dot) + lin * (p[c][i] - o));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < KC; ++c)
+      *reinterpret_cast<float4*>(dn + c * V + v) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // metrics: argmax mask (first maximum wins, like torch.argmax) + 4x4 confusion histogram H[pred][true] (int64)
 // ------------------------------------------------------------------------------------------------
@@ -304,8 +428,13 @@ int b3d_loss_bwd(const float* prob, const float* E, const long long* target, con
   LossCfg cfg;
   memcpy(&cfg, cfg11, sizeof(cfg));
   const long long V = (long long)D * H * W;
-  dim3 grid(std::max(1, ls_blocks(V, 256) / std::max(1, N)), N);
-  loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, E, target, acc, gscale, wscale, dlogits, N, D, H, W, cfg); ++g_b3d_launches;
+  if (W % 4 == 0 && (((uintptr_t)prob | (uintptr_t)dlogits | (uintptr_t)E) & 15) == 0 && ((uintptr_t)target & 15) == 0) {
+    dim3 grid(std::max(1, ls_blocks(V / 4, 256) / std::max(1, N)), N);
+    loss_bwd_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, E, target, acc, gscale, wscale, dlogits, N, D, H, W, cfg); ++g_b3d_launches;
+  } else {
+    dim3 grid(std::max(1, ls_blocks(V, 256) / std::max(1, N)), N);
+    loss_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, E, target, acc, gscale, wscale, dlogits, N, D, H, W, cfg); ++g_b3d_launches;
+  }
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

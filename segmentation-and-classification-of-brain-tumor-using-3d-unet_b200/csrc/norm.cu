@@ -52,6 +52,49 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
   const bf16* yn = y + (long long)n * V * ldy;
   const bf16* rn = (RES != 0) ? r + (long long)n * V * ldr : nullptr;
   bf16* on = out + (long long)n * V * ldo;
+  if ((blockDim.x % C8) == 0) {
+    // the thread's 8-channel chunk never changes (stride is a multiple of C8): keep the coefficients in registers
+    // (the shared-memory path below has 4-way bank conflicts: lanes read floats 8 apart)
+    const int c0 = (int)(threadIdx.x % C8) * 8;
+    float k1[8], k2[8], k3[8], k4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { k1[j] = sc[c0 + j]; k2[j] = sh[c0 + j]; k3[j] = (RES == 1) ? scr[c0 + j] : 0.f; k4[j] = (RES == 1) ? shr[c0 + j] : 0.f; }
+    const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+    long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+    for (; vox + vstep < V; vox += 2 * vstep) {  // two independent voxels per iteration
+      float a[8], a2[8], b[8], b2[8];
+      const uint4 u0 = ldg16_stream(yn + vox * ldy + c0), u1 = ldg16_stream(yn + (vox + vstep) * ldy + c0);
+      uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+      if (RES != 0) { w0 = ldg16_stream(rn + vox * ldr + c0); w1 = ldg16_stream(rn + (vox + vstep) * ldr + c0); }
+      unpack8(u0, a); unpack8(u1, a2);
+      if (RES != 0) { unpack8(w0, b); unpack8(w1, b2); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(a[j], k1[j], k2[j]), t2 = fmaf(a2[j], k1[j], k2[j]);
+        if (RELU) { t = fmaxf(t, 0.f); t2 = fmaxf(t2, 0.f); }
+        if (RES == 1) { t += fmaf(b[j], k3[j], k4[j]); t2 += fmaf(b2[j], k3[j], k4[j]); }
+        if (RES == 2) { t += b[j]; t2 += b2[j]; }
+        a[j] = t; a2[j] = t2;
+      }
+      stg16(on + vox * ldo + c0, pack8(a));
+      stg16(on + (vox + vstep) * ldo + c0, pack8(a2));
+    }
+    if (vox < V) {
+      float a[8], b[8];
+      unpack8(ldg16_stream(yn + vox * ldy + c0), a);
+      if (RES != 0) unpack8(ldg16_stream(rn + vox * ldr + c0), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(a[j], k1[j], k2[j]);
+        if (RELU) t = fmaxf(t, 0.f);
+        if (RES == 1) t += fmaf(b[j], k3[j], k4[j]);
+        if (RES == 2) t += b[j];
+        a[j] = t;
+      }
+      stg16(on + vox * ldo + c0, pack8(a));
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long vox = i / C8;
     const int c0 = (int)(i - vox * C8) * 8;
@@ -75,7 +118,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
 
 // phase 1: sums[n][c][0] += Σ_v dz ; sums[n][c][1] += Σ_v dz*xhat        (dz = dy * relu-mask)
 template <bool RELU>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
     const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y, long long ldy,
     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
     double* __restrict__ sums, long long V, int C, float eps) {
@@ -101,6 +144,31 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
   int myc0 = -1;
+  if (fixed) {
+    const int c0 = (int)(threadIdx.x % C8) * 8;
+    float ka[8], kb[8], kg[8], kbe[8];  // xhat = x*ka + kb ; relu test on xhat*gamma + beta
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ka[j] = s_rstd[c0 + j]; kb[j] = -s_mean[c0 + j] * s_rstd[c0 + j]; kg[j] = s_g[c0 + j]; kbe[j] = s_b[c0 + j]; }
+    const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+    long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+    for (; vox < V; vox += 2 * vstep) {
+      const bool two = vox + vstep < V;
+      const long long vox2 = two ? vox + vstep : vox;
+      float d[8], x[8], d2[8], x2[8];
+      const uint4 ud = ldg16_stream(dyn + vox * lddy + c0), ux = ldg16_stream(yn + vox * ldy + c0);
+      const uint4 ud2 = ldg16_stream(dyn + vox2 * lddy + c0), ux2 = ldg16_stream(yn + vox2 * ldy + c0);
+      unpack8(ud, d); unpack8(ux, x); unpack8(ud2, d2); unpack8(ux2, x2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(x[j], ka[j], kb[j]), xh2 = fmaf(x2[j], ka[j], kb[j]);
+        float dz = d[j], dz2 = two ? d2[j] : 0.f;
+        if (RELU && fmaf(xh, kg[j], kbe[j]) <= 0.f) dz = 0.f;
+        if (RELU && fmaf(xh2, kg[j], kbe[j]) <= 0.f) dz2 = 0.f;
+        a1[j] += dz + dz2; a2[j] = fmaf(dz, xh, fmaf(dz2, xh2, a2[j]));
+      }
+    }
+    myc0 = c0;
+  } else
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long vox = i / C8;
     const int c0 = (int)(i - vox * C8) * 8;
@@ -139,7 +207,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(
 
 // phase 2: dx = A_c*dz − B_g − xhat*Cg ; optionally accumulates into dx (dx += ...)
 template <bool RELU, bool ACC>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
     const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y, long long ldy,
     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
     const double* __restrict__ sums, bf16* __restrict__ dx, long long lddx, long long V, int C, float eps) {
@@ -167,6 +235,38 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(
   const bf16* dyn = dy + (long long)n * V * lddy;
   const bf16* yn = y + (long long)n * V * ldy;
   bf16* dxn = dx + (long long)n * V * lddx;
+  if ((blockDim.x % C8) == 0) {
+    const int c0 = (int)(threadIdx.x % C8) * 8;
+    float ka[8], kb[8], kg[8], kbe[8], kA[8], kB[8], kC[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ka[j] = s_rstd[c0 + j]; kb[j] = -s_mean[c0 + j] * s_rstd[c0 + j]; kg[j] = s_g[c0 + j]; kbe[j] = s_b[c0 + j];
+      kA[j] = s_g[c0 + j] * s_rstd[c0 + j]; kB[j] = s_B[c0 + j]; kC[j] = s_C[c0 + j];
+    }
+    const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+    long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+    for (; vox < V; vox += 2 * vstep) {
+      const bool two = vox + vstep < V;
+      const long long vox2 = two ? vox + vstep : vox;
+      float d[8], x[8], o[8], d2[8], x2[8], o2[8];
+      const uint4 ud = ldg16_stream(dyn + vox * lddy + c0), ux = ldg16_stream(yn + vox * ldy + c0);
+      const uint4 ud2 = ldg16_stream(dyn + vox2 * lddy + c0), ux2 = ldg16_stream(yn + vox2 * ldy + c0);
+      if (ACC) { unpack8(ldg16(dxn + vox * lddx + c0), o); unpack8(ldg16(dxn + vox2 * lddx + c0), o2); }
+      unpack8(ud, d); unpack8(ux, x); unpack8(ud2, d2); unpack8(ux2, x2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(x[j], ka[j], kb[j]), xh2 = fmaf(x2[j], ka[j], kb[j]);
+        float dz = d[j], dz2 = d2[j];
+        if (RELU && fmaf(xh, kg[j], kbe[j]) <= 0.f) dz = 0.f;
+        if (RELU && fmaf(xh2, kg[j], kbe[j]) <= 0.f) dz2 = 0.f;
+        const float v = dz * kA[j] - kB[j] - xh * kC[j], v2 = dz2 * kA[j] - kB[j] - xh2 * kC[j];
+        o[j] = ACC ? o[j] + v : v; o2[j] = ACC ? o2[j] + v2 : v2;
+      }
+      stg16(dxn + vox * lddx + c0, pack8(o));
+      if (two) stg16(dxn + vox2 * lddx + c0, pack8(o2));
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long vox = i / C8;
     const int c0 = (int)(i - vox * C8) * 8;

@@ -151,6 +151,26 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const bf16* __restrict
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   int myc0 = -1;
+  if (fixed) {  // fixed channel chunk per thread: 4 independent 16-byte loads in flight
+    const int c0 = (int)(threadIdx.x % C8) * 8;
+    const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+    long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+    for (; vox + 3 * vstep < V; vox += 4 * vstep) {
+      const uint4 u0 = ldg16_stream(xn + vox * ldx + c0), u1 = ldg16_stream(xn + (vox + vstep) * ldx + c0);
+      const uint4 u2 = ldg16_stream(xn + (vox + 2 * vstep) * ldx + c0), u3 = ldg16_stream(xn + (vox + 3 * vstep) * ldx + c0);
+      float a[8], b[8], c[8], d[8];
+      unpack8(u0, a); unpack8(u1, b); unpack8(u2, c); unpack8(u3, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (a[j] + b[j]) + (c[j] + d[j]);
+    }
+    for (; vox < V; vox += vstep) {
+      float a[8];
+      unpack8(ldg16_stream(xn + vox * ldx + c0), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+    myc0 = c0;
+  } else
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long vox = i / C8;
     const int c0 = (int)(i - vox * C8) * 8;
