@@ -23,7 +23,7 @@
 #include "b3d_internal.h"
 #include <algorithm>
 
-#define ZS_THREADS 192
+#define ZS_THREADS 352   // warp 0 TMA, warps 1 and 6 MMA issuers (ping-pong), warps 2-5 and 7-10 epilogue (even / odd planes)
 #define ZS_MAXSTAGES 8
 #define ZS_BW 10
 #define ZS_BH 18
@@ -85,24 +85,26 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
   const uint32_t tempty0 = tfull0 + 8 * 32;              // [32]
   const uint32_t wfull = tempty0 + 8 * 32;
   const uint32_t wfree = wfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 16);
-  float* s_stats = reinterpret_cast<float*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 32);  // [2 * 64]
+  const uint32_t hs0 = wfree + 8;                        // [2] issue hand-shake between the two MMA warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 32);
+  float* s_stats = reinterpret_cast<float*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 48);  // [2 * 64]
 
   if (threadIdx.x == 0) {
     if (sW & 1023u) { if (P.err) atomicExch(P.err, 29); __trap(); }
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     for (int i = 0; i < R; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
     mbar_init(wfull, 1);
-    mbar_init(wfree, 1);
+    mbar_init(wfree, 2);
+    mbar_init(hs0, 1); mbar_init(hs0 + 8, 1);
     mbar_fence_init();
   }
-  if (threadIdx.x >= 64) s_stats[threadIdx.x - 64] = 0.f;
+  if (threadIdx.x >= 64 && threadIdx.x < 192) s_stats[threadIdx.x - 64] = 0.f;
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2) {  // zero the whole accumulator ring once (TMEM is not cleared by allocation)
+  if (warp >= 2 && warp < 6) {  // zero the whole accumulator ring once (TMEM is not cleared by allocation)
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < 512; c += 16) tmem_st16_zero(lane_base + c);
@@ -152,19 +154,29 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================= MMA issuer (warp-uniform control flow, one elected lane issues) =======================
-    const uint64_t hiA = umma_desc_hi_sw((uint32_t)ZS_BW * RB, LT) | (1ull << 16);   // groups of 8 x-positions, SBO = one tile row
-    const uint64_t hiB = umma_desc_hi_sw(8u * RB, LT) | (1ull << 16);
+  } else if (warp == 1 || warp == 6) {
+    // ======================= MMA issuers (warp-uniform control flow, one elected lane issues) =======================
+    // The per-plane bookkeeping below is deliberately lean (32-bit ring arithmetic, one barrier wait and one commit in
+    // the steady state): the tensor pipe only queues a few MMAs, so every scalar instruction between two planes is idle
+    // tensor time (profiles/ncu_zs_r1: 408 instructions per plane before this rewrite = 60 % idle).
+    const uint64_t hiA = umma_desc_hi_sw((uint32_t)ZS_BW * RB, LT);   // groups of 8 x-positions, SBO = one tile row
+    const uint64_t hiB = umma_desc_hi_sw(8u * RB, LT);
     const uint32_t idesc1 = umma_idesc_bf16(128, COUT, 0, 0);
     const uint32_t idesc2 = umma_idesc_bf16(128, 2 * COUT, 0, 0);
     const uint32_t idesc3 = umma_idesc_bf16(128, 3 * COUT, 0, 0);
+    constexpr uint32_t RM = R - 1;
+    constexpr uint32_t LBO1 = 1u << 16;   // descriptor LBO field (unused for swizzled K-major, conventionally 1)
     uint32_t s = 0, ph = 0;
-    long long g0 = 0;  // running count of output planes of this CTA (selects ring slot and barrier phase)
+    uint32_t g0 = 0;  // running count of output planes of this CTA (selects ring slot and barrier phase)
+    uint32_t pc = 0;  // running count of input planes (alternates between the two issuer warps)
+    const uint32_t role = (warp == 1) ? 0u : 1u;
     int cur_nb = -1;
     uint32_t wloads = 0;
     long long pos = lo;
     ZsSeg sg;
+    auto wait_fresh = [&](uint32_t g) {   // the epilogue has drained + zeroed the slot that plane g re-uses
+      mbar_wait(tempty0 + 8 * (g & RM), (((g / R) & 1u) ^ 1u), P.err, 24);
+    };
     while (zs_next_seg(pos, hi, P.D, sg)) {
       const int nb = sg.col / P.tiles_per_nb;
       if (nb != cur_nb) {
@@ -173,27 +185,26 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
         cur_nb = nb; ++wloads;
       }
       const int L = sg.zb - sg.za;
-      const int zi0 = sg.za > 0 ? sg.za - 1 : 0;
-      const int zi1 = sg.zb < P.D ? sg.zb : P.D - 1;
-      for (int zi = zi0; zi <= zi1; ++zi) {
-        const int i = zi - (sg.za - 1);                 // 0 .. L+1
+      const int i_min = sg.za > 0 ? 0 : 1;            // plane index i <-> input plane z = za - 1 + i
+      const int i_max = sg.zb < P.D ? L + 1 : L;
+      // Two issuer warps alternate planes: while one is blocked feeding its plane's MMAs into the (shallow) tensor queue,
+      // the other does the barrier waits / ring arithmetic of the next plane, then issues right behind it.  The tensor
+      // pipe executes in issue order, so accumulations into shared ring slots stay ordered; hs[r] = "warp r has issued".
+      for (int i = i_min; i <= i_max; ++i, ++pc) {
+        if ((pc & 1u) != role) {   // the other warp's plane: only keep the stage ring position in step
+          for (int kc = 0; kc < P.k_chunks; ++kc) if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+          continue;
+        }
         const int o_hi = i < L - 1 ? i : L - 1;         // newest target (smallest kd)
         const int o_lo = i - 2 > 0 ? i - 2 : 0;         // oldest target
         const int cnt = o_hi - o_lo + 1;                // 1..3 targets
         const int kd0 = i - o_hi;                       // kd of the newest target
-        // fresh targets (first contribution): wait until the epilogue has drained + zeroed their slot
-        for (int o = o_lo; o <= o_hi; ++o) {
-          const int first_i = (o > zi0 - (sg.za - 1)) ? o : zi0 - (sg.za - 1);
-          if (first_i == i) {
-            const long long g = g0 + o;
-            const uint32_t slot = (uint32_t)(g % R), use = (uint32_t)(g / R);
-            mbar_wait(tempty0 + 8 * slot, (use & 1u) ^ 1u, P.err, 24);
-          }
-        }
-        tc_fence_after();
+        // targets that receive their first contribution from this plane
+        if (i == i_min) { for (int o = o_lo; o <= o_hi; ++o) wait_fresh(g0 + (uint32_t)o); }
+        else if (i <= L - 1) wait_fresh(g0 + (uint32_t)i);
         // column runs: target o_hi - j sits at ring position R-1-((g_hi - j) mod R) = p0 + j until it wraps to 0
-        const uint32_t m = (uint32_t)((g0 + o_hi) % R);
-        const uint32_t p0 = (uint32_t)(R - 1) - m;
+        const uint32_t m = (g0 + (uint32_t)o_hi) & RM;
+        const uint32_t p0 = RM - m;
         const int run1 = (cnt <= (int)m + 1) ? cnt : (int)m + 1;
         const int run2 = cnt - run1;                     // wrapped part, starts at ring position 0
         const uint32_t d1 = tmem_base + p0 * COUT;
@@ -202,10 +213,10 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
         const uint32_t id2 = run2 == 2 ? idesc2 : idesc1;
         for (int kc = 0; kc < P.k_chunks; ++kc) {
           mbar_wait(full0 + 8 * s, ph, P.err, 23);
+          if (kc == 0 && pc > 0) mbar_wait(hs0 + 8 * (role ^ 1u), ((pc - 1u) >> 1) & 1u, P.err, 26);  // previous plane issued
           tc_fence_after();
-          const uint32_t a16 = (sA + s * A_STAGE) >> 4;
-          const uint32_t w16 = ((sW + kc * W_CHUNK) >> 4) + (uint32_t)(kd0 * COUT) * rb16;
-          const uint32_t w16b = w16 + (uint32_t)(run1 * COUT) * rb16;
+          const uint32_t a16 = ((sA + s * A_STAGE) >> 4) | LBO1;
+          const uint32_t w16 = (((sW + kc * W_CHUNK) >> 4) + (uint32_t)(kd0 * COUT) * rb16) | LBO1;
           if (elect_one()) {
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
@@ -220,6 +231,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
               }
             }
             if (run2 > 0) {
+              const uint32_t w16b = w16 + (uint32_t)(run1 * COUT) * rb16;
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -233,24 +245,21 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
                 }
               }
             }
+            if (kc == P.k_chunks - 1) mbar_arrive(hs0 + 8 * role);   // this plane is in the tensor queue
             umma_commit(empty0 + 8 * s);
+            // targets whose last contribution was this plane are complete
+            if (kc == P.k_chunks - 1) {
+              if (i == i_max) { for (int o = o_lo; o <= o_hi; ++o) umma_commit(tfull0 + 8 * ((g0 + (uint32_t)o) & RM)); }
+              else if (i >= 2) umma_commit(tfull0 + 8 * ((g0 + (uint32_t)(i - 2)) & RM));
+            }
           }
           __syncwarp();
           if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
-        // targets whose last contribution was this plane are complete
-        for (int o = o_lo; o <= o_hi; ++o) {
-          const int last_i = (o + 2 < zi1 - (sg.za - 1)) ? o + 2 : zi1 - (sg.za - 1);
-          if (last_i == i) {
-            const uint32_t slot = (uint32_t)((g0 + o) % R);
-            if (elect_one()) umma_commit(tfull0 + 8 * slot);
-            __syncwarp();
-          }
-        }
       }
-      g0 += L;
+      g0 += (uint32_t)L;
       // the next segment may bring other weights: tell the producer when this segment's MMAs no longer read them
-      {
+      if (P.n_blocks > 1) {
         long long p2 = pos; ZsSeg nx;
         if (zs_next_seg(p2, hi, P.D, nx) && nx.col / P.tiles_per_nb != nb) {
           if (elect_one()) umma_commit(wfree);
@@ -259,11 +268,13 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =======================
+    // ======================= epilogue: warps 2..5 drain even output planes, warps 7..10 odd ones =======================
+    // (TMEM lane quadrant = warp % 4; two groups because one plane's drain + bf16 store costs more than its MMAs at small Cin)
     const int q = warp & 3;
+    const uint32_t grp = (warp >= 7) ? 1u : 0u;
     const int row = q * 32 + lane;
     const int yl = row >> 3, xl = row & 7;   // M row -> voxel of the 16x8 patch
-    const int et = threadIdx.x - 64;         // 0..127
+    const int et = grp ? 9999 : (int)threadIdx.x - 64;   // group-0 threads 0..127 publish the statistics
     const int cpg = P.cpg;
     const bool fine = (cpg < 4);             // statistics granule: 4 channels (cpg % 4 == 0) or 1 channel
     constexpr int NACC = COUT / 4 > 16 ? COUT / 4 : 16;
@@ -271,7 +282,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    long long g0 = 0;
+    const bool has_stats = P.stats != nullptr, has_bias = P.bias != nullptr;
+    uint32_t g0 = 0;
     long long pos = lo;
     ZsSeg sg;
     while (zs_next_seg(pos, hi, P.D, sg)) {
@@ -282,10 +294,14 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
       const int y = ty * 16 + yl, x = tx * 8 + xl;
       const bool valid = (y < P.H) && (x < P.W);
       const int c_base = nb * COUT;
+      const bool full = (c_base + COUT <= P.Cout);
       const int L = sg.zb - sg.za;
+      bf16* op0 = P.out + ((((long long)n * P.D + sg.za) * P.H + y) * P.W + x) * P.ld_out + c_base;
+      const long long plane_stride = (long long)P.H * P.W * P.ld_out;
       for (int o = 0; o < L; ++o) {
-        const long long g = g0 + o;
-        const uint32_t slot = (uint32_t)(g % R), use = (uint32_t)(g / R);
+        const uint32_t g = g0 + (uint32_t)o;
+        if ((g & 1u) != grp) continue;
+        const uint32_t slot = g % R, use = g / R;
         const uint32_t pcol = (uint32_t)(R - 1 - slot) * COUT;
         mbar_wait(tfull0 + 8 * slot, use & 1u, P.err, 25);
         tc_fence_after();
@@ -299,37 +315,52 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
-        const int zo = sg.za + o;
-        const long long vox = (((long long)n * P.D + zo) * P.H + y) * P.W + x;
-        bf16* op = P.out + vox * P.ld_out + c_base;
+        bf16* op = op0 + (long long)o * plane_stride;
 #pragma unroll
-        for (int j0 = 0; j0 < COUT; j0 += 8) {
-          float v[8];
+        for (int j0 = 0; j0 < COUT; j0 += 16) {
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f = __uint_as_float(r[j0 + j]);
-            if (P.bias != nullptr && c_base + j0 + j < P.Cout) f += __ldg(P.bias + c_base + j0 + j);
-            v[j] = f;
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j0 + j]);
+          if (has_bias) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + c_base + j0 + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (c_base + j0 + j < P.Cout) v[j] += __ldg(P.bias + c_base + j0 + j);
+            }
           }
           if (valid) {
-            if (P.stats != nullptr) {
+            if (has_stats) {
               if (!fine) {
-                a1[j0 / 4] += (v[0] + v[1]) + (v[2] + v[3]);
-                a2[j0 / 4] += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
-                a1[j0 / 4 + 1] += (v[4] + v[5]) + (v[6] + v[7]);
-                a2[j0 / 4 + 1] += (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
-              } else if (j0 < 16) {  // per-channel granule: only the first 16 channels of a block are supported (COUT == 16)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { a1[j0 + j] += v[j]; a2[j0 + j] += v[j] * v[j]; }
+                for (int qd = 0; qd < 4; ++qd) {
+                  a1[j0 / 4 + qd] += (v[4 * qd] + v[4 * qd + 1]) + (v[4 * qd + 2] + v[4 * qd + 3]);
+                  a2[j0 / 4 + qd] += (v[4 * qd] * v[4 * qd] + v[4 * qd + 1] * v[4 * qd + 1]) +
+                                     (v[4 * qd + 2] * v[4 * qd + 2] + v[4 * qd + 3] * v[4 * qd + 3]);
+                }
+              } else if (j0 == 0) {  // per-channel granule: only the first 16 channels of a block (COUT == 16)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { a1[j] += v[j]; a2[j] = fmaf(v[j], v[j], a2[j]); }
               }
             }
-            if (c_base + j0 + 8 <= P.Cout) stg16(op + j0, pack8(v));
+            if (full && ((reinterpret_cast<uintptr_t>(op + j0) & 31) == 0)) {
+              const uint4 u0 = pack8(v), u1 = pack8(v + 8);
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + j0), "r"(u0.x), "r"(u0.y), "r"(u0.z),
+                           "r"(u0.w), "r"(u1.x), "r"(u1.y), "r"(u1.z), "r"(u1.w) : "memory");
+            } else {
+              if (c_base + j0 + 8 <= P.Cout) stg16(op + j0, pack8(v));
+              if (c_base + j0 + 16 <= P.Cout) stg16(op + j0 + 8, pack8(v + 8));
+            }
           }
         }
       }
-      g0 += L;
+      g0 += (uint32_t)L;
       // flush this segment's statistics (one sample, one output-channel block)
-      if (P.stats != nullptr) {
+      if (has_stats) {
         const int gran = fine ? 1 : 4;
         const int nacc = fine ? 16 : COUT / 4;
 #pragma unroll
@@ -344,7 +375,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
           }
           a1[i] = 0.f; a2[i] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int groups_blk = (COUT + cpg - 1) / cpg;
         if (et < 2 * groups_blk) {
           const int gi = c_base / cpg + (et >> 1);
@@ -354,7 +385,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
           }
           s_stats[et] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }
