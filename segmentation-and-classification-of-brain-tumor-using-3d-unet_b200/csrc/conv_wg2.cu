@@ -330,6 +330,7 @@ int b3d_try_wg2(const void* x, long long ldx, int Cin, const void* dy, long long
     if (rc) return rc;
   }
   const size_t smem = WG2_R * xs + 2 * ys + 1024 + 256 + 1024;
+  B3D_CHECK_CUDA(cudaMemsetAsync(dwacc, 0, (size_t)27 * Cin_pad * Cout_pad * 4, stream));
   const int num_sms = b3d_num_sms();
   const int grid = (int)std::min<long long>(num_sms, P.total_steps);
   if (getenv("B3D_VERBOSE"))

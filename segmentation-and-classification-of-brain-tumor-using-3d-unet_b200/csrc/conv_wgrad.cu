@@ -38,6 +38,7 @@ struct alignas(64) WgradParams {
   float* dwacc;
   int Cin, Cout, Cout_pad, Cin_pad;
   int tmem_cols;
+  int exclusive;    // every key is processed by exactly one CTA: flush with plain stores (no memset, no atomics)
   int* err;
 };
 
@@ -269,7 +270,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             uint32_t rr[16];
             tmem_ld16(trow + j0, rr);
             tmem_ld_wait();
-            if (row_ok && ((started >> chain) & 1u)) {
+            if (P.exclusive) {
+              if (row_ok && k.cob * P.BN + j0 + 16 <= P.Cout_pad) {
+                const bool live = (started >> chain) & 1u;   // chains that never received an MMA hold stale TMEM: store zeros
+                float4* d4 = reinterpret_cast<float4*>(dst + j0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  d4[j] = live ? make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]),
+                                             __uint_as_float(rr[4 * j + 3]))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            } else if (row_ok && ((started >> chain) & 1u)) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (k.cob * P.BN + j0 + j < P.Cout_pad) atomicAdd(dst + j0 + j, __uint_as_float(rr[j]));
@@ -291,16 +302,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 
 // dwacc fp32 [taps][Cin_pad][Cout_pad] -> reference layouts (fp32), optionally accumulating into an existing gradient
 //   mode 0: conv   dW[co][ci][tap]           mode 1: convT  dWt[ci][co][t8]
-__global__ void wgrad_finalize_kernel(const float* __restrict__ acc, float* __restrict__ dw, int mode, int ntaps, int Cin,
-                                      int Cout, int Cin_pad, int Cout_pad, int accumulate) {
-  const long long total = (long long)ntaps * Cin * Cout;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    int tap, ci, co;
-    if (mode == 0) { tap = (int)(t % ntaps); t /= ntaps; ci = (int)(t % Cin); co = (int)(t / Cin); }
-    else { tap = (int)(t % ntaps); t /= ntaps; co = (int)(t % Cout); ci = (int)(t / Cout); }
-    const float v = acc[((long long)tap * Cin_pad + ci) * Cout_pad + co];
-    dw[i] = accumulate ? dw[i] + v : v;
+// One block per (ci, 32 output channels): coalesced 128-byte reads of dwacc rows, smem transpose, runs of `ntaps`
+// consecutive floats on the write side.
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ acc, float* __restrict__ dw, int mode,
+                                                             int ntaps, int Cin, int Cout, int Cin_pad, int Cout_pad,
+                                                             int accumulate) {
+  __shared__ float tile[27][33];
+  const int cob = blockIdx.x, ci = blockIdx.y;
+  const int co0 = cob * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int tap = w; tap < ntaps; tap += 8) {
+    const int co = co0 + lane;
+    tile[tap][lane] = (co < Cout) ? acc[((long long)tap * Cin_pad + ci) * Cout_pad + co] : 0.f;
+  }
+  __syncthreads();
+  const int nco = min(32, Cout - co0);
+  for (int idx = threadIdx.x; idx < nco * ntaps; idx += 256) {
+    const int col = idx / ntaps, tap = idx - col * ntaps;
+    const int co = co0 + col;
+    const long long o = (mode == 0) ? ((long long)co * Cin + ci) * ntaps + tap : ((long long)ci * Cout + co) * ntaps + tap;
+    const float v = tile[tap][col];
+    dw[o] = accumulate ? dw[o] + v : v;
   }
 }
 
@@ -401,6 +423,13 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
   P.num_items = P.items_per_key * P.num_keys;
   const int grid = std::min(P.num_items, num_sms);
   P.items_per_cta = (P.num_items + grid - 1) / grid;
+  // many keys: give every CTA whole keys, so that the flush needs neither a zeroed accumulator nor atomics
+  if (P.items_per_cta % P.items_per_key != 0 && P.num_keys * 2 >= num_sms)
+    P.items_per_cta = (P.items_per_cta + P.items_per_key - 1) / P.items_per_key * P.items_per_key;
+  P.exclusive = (P.items_per_cta % P.items_per_key == 0) ? 1 : 0;
+  if (getenv("B3D_WG_NOEXCL")) P.exclusive = 0;
+  if (!P.exclusive)
+    B3D_CHECK_CUDA(cudaMemsetAsync(dwacc, 0, (size_t)(ks == 3 ? 27 : (nmapsY > 1 ? nmapsY : 1)) * Cin_pad * Cout_pad * 4, stream));
   const int grid2 = (P.num_items + P.items_per_cta - 1) / P.items_per_cta;
   P.dwacc = dwacc; P.err = err_flag;
 
@@ -472,7 +501,6 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   B3D_REQUIRE(lddy >= Cout_pad || Cout_pad == Cout, "conv_wgrad: dy must expose %d (padded) channels", Cout_pad);
   const size_t need = (size_t)ntaps * Cin * Cout_pad * 4;
   B3D_REQUIRE(ws_bytes >= need, "conv_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
-  B3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, st));
   int n = N, d = D, h = H, w = W;
   if (ks == 1) {  // pointwise: flatten every voxel of the batch into rows of up to 128 positions
     const long long V = (long long)N * D * H * W;
@@ -498,9 +526,7 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   if (rc < 0) return rc;
   if (rc > 0) rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
-  const long long total = (long long)ntaps * Cin_real * Cout;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
+  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, Cin_real), 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -513,7 +539,6 @@ int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long ldd
   B3D_REQUIRE(Cout_pad == Cout, "convT2_wgrad: Cout must be a multiple of 16");
   const size_t need = (size_t)8 * Cin * Cout_pad * 4;
   B3D_REQUIRE(ws_bytes >= need, "convT2_wgrad: workspace too small");
-  B3D_CHECK_CUDA(cudaMemsetAsync(ws, 0, need, st));
   YView yv[8];
   const long long pW = lddy * 2, pH = pW * (2 * W), pD = pH * (2 * H);
   for (int t8 = 0; t8 < 8; ++t8) {
@@ -524,9 +549,7 @@ int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long ldd
   // the N*D planes of the coarse grid: plane (n,z) of view t8 starts at n*(2D)*pD + 2z*pD = (n*D+z)*2*pD  -> uniform stride
   int rc = run_wgrad(x, ldx, Cin, yv, 8, N, D, H, W, Cout, 1, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
-  const long long total = (long long)8 * Cin * Cout;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  wgrad_finalize_kernel<<<blocks, 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
+  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, Cin), 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

@@ -52,7 +52,21 @@ def _oracle_train(sd, x, y, feats, masks=None):
     return main.detach(), [d.detach() for d in deep], float(loss), {k: v.grad for k, v in sdg.items()}, bn
 
 
-def _check_grads(model, ref_grads, tag):
+def _oracle_autocast_grads(sd, x, y, feats, masks=None):
+    """The oracle's OWN bf16-autocast gradients (run on the GPU): the per-tensor error bar the reference's numerics allow
+    (SURVEY hard part 5: at 32^3 the reference under autocast is itself 20-30 % off fp32 in the deep blocks)."""
+    sdg = {k: v.clone().to(DEV).requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        main, deep, _ = O.unet_forward(x.to(DEV), sdg, feats, training=True,
+                                       dropout_masks=None if masks is None else [m.to(DEV) for m in masks])
+    O.deep_supervision_loss(main.float(), [d.float() for d in deep], y.to(DEV)).backward()
+    return {k: (v.grad.cpu() if v.grad is not None else None) for k, v in sdg.items()}
+
+
+def _check_grads(model, ref_grads, tag, autocast_grads=None):
+    """Per tensor: cosine >= 0.9 and rel-L2 <= max(0.10, 1.6 x the oracle's own bf16-autocast rel-L2) (0.35 absolute when no
+    autocast reference is given); whole model: cosine >= 0.99.  Measured (scripts/grad_error_report.py, 2x32^3, dropout):
+    worst tensor 0.347 vs 0.284 for the autocast oracle (ratio 1.22), median 0.015 vs 0.019; run-to-run jitter ~0.005."""
     tot = np.sqrt(sum(float(g.double().norm()) ** 2 for g in ref_grads.values() if g is not None))
     dots = n1 = n2 = 0.0
     worst = (1.0, 0.0, None)
@@ -70,7 +84,8 @@ def _check_grads(model, ref_grads, tag):
             c, r = _cos(g, rg), _rel_l2(g, rg)
             if c < worst[0]:
                 worst = (c, r, k)
-            assert c >= 0.9 and r <= 0.35, "%s: grad cos %.4f rel-L2 %.4f" % (k, c, r)
+            lim = 0.35 if autocast_grads is None else max(0.10, 1.6 * _rel_l2(autocast_grads[k], rg))
+            assert c >= 0.9 and r <= lim, "%s: grad cos %.4f rel-L2 %.4f (limit %.4f)" % (k, c, r, lim)
     total_cos = dots / (np.sqrt(n1 * n2) + 1e-30)
     REPORT[tag + "_grad_total_cos"] = total_cos
     REPORT[tag + "_grad_worst"] = worst
@@ -115,7 +130,7 @@ def test_unet_eval_and_train_vs_golden_and_oracle(golden, golden_arrays, case):
     assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
     for i in range(4):
         assert _rel_l2(deep[i].detach().cpu(), rdeep[i]) <= 2.5e-2, i
-    _check_grads(model, rgrads, case)
+    _check_grads(model, rgrads, case, _oracle_autocast_grads(sd, x, y, feats))
     np.testing.assert_allclose(model.final_conv[1].running_mean.cpu().numpy(), rbn[0].detach().numpy(), rtol=2e-2, atol=2e-3)
     np.testing.assert_allclose(model.final_conv[1].running_var.cpu().numpy(), rbn[1].detach().numpy(), rtol=2e-2, atol=2e-3)
     assert int(model.final_conv[1].num_batches_tracked) == 1
@@ -144,7 +159,7 @@ def test_unet_dropout_uses_torch_rng_stream():
     rmain, rdeep, rloss, rgrads, _ = _oracle_train(sd, x, y, feats, masks=masks)
     assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
     assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss)
-    _check_grads(model, rgrads, "dropout")
+    _check_grads(model, rgrads, "dropout", _oracle_autocast_grads(sd, x, y, feats, masks=masks))
 
 
 def test_default_architecture_train_step(golden):
