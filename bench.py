@@ -43,19 +43,43 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Polls NVML in-process every
+    10 ms (a 5-step timed region lasts ~0.1 s, shorter than nvidia-smi's start-up); falls back to `nvidia-smi -lms`."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def run(self):
         try:
+            nv, h = self._nvml_handle()
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                act = lambda bit: "Active" if (rs & bit) else "Not Active"
+                self.rows.append([str(sm), str(mx), "0", act(0x8), act(0x40), act(0x20), act(0x4)])
+                time.sleep(0.01)
+            return
+        except Exception:
+            pass
+        try:
             p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                  "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return
         self.proc = p
@@ -70,9 +94,10 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         self.stop_flag = True
-        time.sleep(0.25)
+        time.sleep(0.05)
         try:
-            self.proc.kill()
+            if self.proc is not None:
+                self.proc.kill()
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
@@ -193,20 +218,30 @@ def main():
     model.train()
     crit = U.DeepSupervisionLoss3D()
     net = DataParallel(model) if world > 1 else model
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    use_graph = not os.environ.get("B3D_NO_GRAPH")
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
 
     g = torch.Generator().manual_seed(1000 + rank)
     x_host = torch.randn(PER_GPU_BATCH, 4, SIZE, SIZE, SIZE, generator=g).pin_memory()
     y_host = torch.randint(0, 4, (PER_GPU_BATCH, SIZE, SIZE, SIZE), generator=g).pin_memory()
     xd, yd = x_host.to(dev), y_host.to(dev)
 
-    def step(xi, yi):
+    def eager_step(xi, yi):
         opt.zero_grad(set_to_none=True)
         out = net(xi)
         loss = crit(out, yi)
         loss.backward()
         opt.step()
         return loss
+
+    step, graphed = eager_step, False
+    if use_graph:  # the whole step (fwd + loss + bwd + all-reduce + AdamW) as ONE CUDA graph, replayed per step
+        try:
+            step = U.GraphedTrainStep(net, crit, opt, xd, yd, warmup=3)
+            graphed = True
+        except Exception as e:  # noqa: BLE001 - fall back to the eager (still all-CUDA) step
+            sys.stderr.write("[bench] CUDA-graph capture failed (%s: %s); running the eager step\n" % (type(e).__name__, e))
+            step = eager_step
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,19 +258,33 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    ops.PROFILE = []
-    l0 = lib.b3d_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.rows.clear()   # keep only samples taken under load
     e0.record()
     for _ in range(args.steps):
         step(xd, yd)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    clocks = sampler.summary() if sampler else None
+    # per-kernel-family CUDA events + launch count: an eager pass of the SAME step right after the timed region (a replayed
+    # CUDA graph has no host-side hooks between its kernels); it is not part of `value`
+    if graphed:
+        for _ in range(2):   # the eager allocator pool is cold after the capture: warm it before timing the eager pass
+            eager_step(xd, yd)
+    ops.PROFILE = []
+    l0 = lib.b3d_launch_count()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eager_step(xd, yd)
+    e1.record()
+    barrier()
+    ms_prof = e0.elapsed_time(e1)
     launches = lib.b3d_launch_count() - l0
     prof, ops.PROFILE = ops.PROFILE, None
-    clocks = sampler.summary() if sampler else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -248,9 +297,12 @@ def main():
     e0.record()
     last = 0.0
     for _ in range(args.steps):
-        xi = x_host.to(dev, non_blocking=True)
-        yi = y_host.to(dev, non_blocking=True)
-        last = step(xi, yi).item()
+        if graphed:   # pinned host -> static device buffers (stream-ordered H2D), replay, read the loss back
+            last = step(x_host, y_host).item()
+        else:
+            xi = x_host.to(dev, non_blocking=True)
+            yi = y_host.to(dev, non_blocking=True)
+            last = step(xi, yi).item()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -265,21 +317,29 @@ def main():
     # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), from CUDA events inside the timed region ----
     peaks = _peaks()
     fam = {}
-    for name, flops, a, b in prof:
+    for name, flops, a, b, tag in prof:
+        # families by kernel: conv3 = 3x3x3 fprop/dgrad (conv_zs.cu at levels 0-1, conv_igemm.cu below), pointwise = 1x1x1
+        # convs + ConvTranspose (conv_igemm.cu), wgrad3 = 3x3x3 weight gradients (conv_wg2.cu / conv_wgrad.cu), wgrad_pw
+        kind = tag.split(" ")[0] if tag else name
+        name = {"conv3": "conv3", "conv1": "pointwise", "convT": "pointwise", "convT_dgrad": "pointwise",
+                "wgrad3": "wgrad3", "wgrad1": "wgrad_pw", "wgradT": "wgrad_pw"}.get(kind, name)
         d = fam.setdefault(name, [0.0, 0.0, 0])
         d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
     roof, fams = None, {}
     for name, (fl, tms, cnt) in fam.items():
         fams[name] = {"tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None, "ms_per_step": tms / args.steps,
                       "launches_per_step": cnt / args.steps, "gflop_per_launch": fl / max(cnt, 1) / 1e9}
-    if "igemm" in fam:
-        fl, tms, cnt = fam["igemm"]
+    if "conv3" in fam:
+        fl, tms, cnt = fam["conv3"]
         ach = fl / (tms * 1e-3) / 1e12
-        roof = {"kernel": "igemm_kernel (conv fprop/dgrad/convT, tcgen05)", "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "zs_kernel / igemm_kernel (3x3x3 conv fprop + dgrad, tcgen05 implicit GEMM)", "bound": "tensor",
+                "achieved": ach,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
                 "traffic": None, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
                 "avg_launch_ms": tms / max(cnt, 1), "algorithmic_gflop_per_launch": fl / max(cnt, 1) / 1e9,
-                "share_of_step": tms / ms}
+                "share_of_step": tms / ms_prof,
+                "measured_in": "eager pass of the same step inside bench.py (CUDA events around every launch), %.2f ms/step"
+                               % (ms_prof / args.steps)}
 
     # ---- inference (cfg 2): batch 1, 4 x 128^3, eval mode ---------------------------------------------------------------
     inference = None
@@ -317,7 +377,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "cfg3: train step, batch 2/GPU, 4x128^3, default arch [32,64,128,256,512], dropout 0.2, "
                                    "DeepSupervisionLoss3D(CombinedLoss3D), step = fwd+loss+bwd(+NCCL grad all-reduce)+fused AdamW",
-                       "global_batch": world * PER_GPU_BATCH, "parallelism": "dp%d" % world,
+                       "global_batch": world * PER_GPU_BATCH, "parallelism": "dp%d" % world, "cuda_graph": graphed,
                        "l2": "no explicit flush: one step streams >5 GB of activations (>> 126 MB L2)"},
             "conv_tflops_whole_step": TRAIN_FLOP_PER_VOXEL * vox_per_step / world / (ms / args.steps * 1e-3) / 1e12,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams,

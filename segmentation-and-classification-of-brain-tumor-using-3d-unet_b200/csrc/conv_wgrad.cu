@@ -151,14 +151,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (warp-uniform control flow, one elected lane issues) =======================
+    {
       const uint32_t idesc = umma_idesc_bf16(128, P.BN, 1, 1);
       const uint32_t lbo = (128u >> 4) << 16;
       const uint64_t hiA = umma_desc_hi(P.plane_mode ? (uint32_t)P.XP * 16u : (uint32_t)P.BW * 16u);
       const uint64_t hiB = umma_desc_hi(P.plane_mode ? (uint32_t)P.YP * 16u : (uint32_t)P.W * 16u);
       uint32_t Q = 0, T = 0, started = 0, flushes = 0;
       int cur_key = -1;
+      const int nkw = (P.halo ? 3 : 1);
       for (int item = item_beg; item < item_end; ++item) {
         const int key = item / P.items_per_key;
         int r = item - key * P.items_per_key;
@@ -170,9 +171,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         const int rows = min(P.TH, P.H - y0);
         if (key != cur_key) {
           if (cur_key >= 0) {
-            *s_started = started;
-            __threadfence_block();
-            umma_commit(accfull);
+            if (elect_one()) {
+              *s_started = started;
+              __threadfence_block();
+              umma_commit(accfull);
+            }
+            __syncwarp();
             mbar_wait(accempty, flushes & 1u, P.err, 13);
             tc_fence_after();
             ++flushes;
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         for (int t = 0; t < nz; ++t) {
           const uint32_t yslot = T & 1u, yph = (T >> 1) & 1u;
           mbar_wait(yfull0 + 8 * yslot, yph, P.err, 14);
-          const uint32_t yb16 = (sY + yslot * P.y_slot_bytes) >> 4;
+          const uint32_t yb16 = ((sY + yslot * P.y_slot_bytes) >> 4) | lbo;
           for (int a = 0; a < P.xspan; ++a) {  // a = kd for variant 0
             const uint32_t q = Q0 + t + a;
             const uint32_t xslot = q % P.R, xph = (q / P.R) & 1u;
@@ -192,50 +196,73 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             tc_fence_after();
             const int z = z0 + t + a + zoff;
             if (z >= 0 && z < P.D) {
-              const uint32_t xb16 = (sX + xslot * P.x_slot_bytes) >> 4;
-              const int nkw = (P.halo ? 3 : 1);
-              if (!P.plane_mode) {
-                for (int y = 0; y < rows; ++y) {
-                  const uint32_t arow = xb16 + (uint32_t)(y * P.CI8) * P.BW;
-                  const uint32_t brow = yb16 + (uint32_t)(y * P.CO8) * P.W;
-                  for (int j = 0; j < P.ksteps; ++j) {
-                    const uint32_t blo = ((brow + j * 16) & 0x3FFFu) | lbo;
-                    for (int kw = 0; kw < nkw; ++kw) {
-                      const int chain = (P.variant == 0) ? a * 3 + kw : kw;
-                      const uint32_t alo = ((arow + j * 16 + kw) & 0x3FFFu) | lbo;
-                      umma_bf16_ss(tmem_base + chain * P.BN, hiA | alo, hiB | blo, idesc, (started >> chain) & 1u);
-                      started |= 1u << chain;
+              const uint32_t xb16 = ((sX + xslot * P.x_slot_bytes) >> 4) | lbo;
+              // chains touched by this plane: variant 0 -> a*3 + kw, else kw
+              const int chain0 = (P.variant == 0) ? a * 3 : 0;
+              const uint32_t d0 = tmem_base + chain0 * P.BN;
+              const uint32_t acc0 = (started >> chain0) & 1u, acc1 = (started >> (chain0 + 1)) & 1u,
+                             acc2 = (started >> (chain0 + 2)) & 1u;
+              if (elect_one()) {
+                uint32_t c0 = acc0, c1 = acc1, c2 = acc2;
+                if (!P.plane_mode) {
+                  for (int y = 0; y < rows; ++y) {
+                    uint32_t alo = xb16 + (uint32_t)(y * P.CI8) * P.BW;
+                    uint32_t blo = yb16 + (uint32_t)(y * P.CO8) * P.W;
+                    if (nkw == 1) {
+                      for (int j = 0; j < P.ksteps; ++j) {
+                        umma_bf16_ss(d0, hiA | alo, hiB | blo, idesc, c0); c0 = 1u;
+                        alo += 16; blo += 16;
+                      }
+                    } else {
+                      for (int j = 0; j < P.ksteps; ++j) {
+                        umma_bf16_ss(d0, hiA | alo, hiB | blo, idesc, c0); c0 = 1u;
+                        umma_bf16_ss(d0 + P.BN, hiA | (alo + 1), hiB | blo, idesc, c1); c1 = 1u;
+                        umma_bf16_ss(d0 + 2 * P.BN, hiA | (alo + 2), hiB | blo, idesc, c2); c2 = 1u;
+                        alo += 16; blo += 16;
+                      }
                     }
                   }
-                }
-              } else {
-                const int khoff = (P.variant == 1) ? k.kh * P.BW : 0;
-                for (int j = 0; j < P.ksteps; ++j) {
-                  const uint32_t blo = ((yb16 + j * 16) & 0x3FFFu) | lbo;
-                  for (int kw = 0; kw < nkw; ++kw) {
-                    const uint32_t alo = ((xb16 + j * 16 + khoff + kw) & 0x3FFFu) | lbo;
-                    umma_bf16_ss(tmem_base + kw * P.BN, hiA | alo, hiB | blo, idesc, (started >> kw) & 1u);
-                    started |= 1u << kw;
+                } else {
+                  const uint32_t khoff = (P.variant == 1) ? (uint32_t)(k.kh * P.BW) : 0u;
+                  uint32_t alo = xb16 + khoff, blo = yb16;
+                  for (int j = 0; j < P.ksteps; ++j) {
+                    umma_bf16_ss(d0, hiA | alo, hiB | blo, idesc, c0); c0 = 1u;
+                    if (nkw == 3) {
+                      umma_bf16_ss(d0 + P.BN, hiA | (alo + 1), hiB | blo, idesc, c1); c1 = 1u;
+                      umma_bf16_ss(d0 + 2 * P.BN, hiA | (alo + 2), hiB | blo, idesc, c2); c2 = 1u;
+                    }
+                    alo += 16; blo += 16;
                   }
                 }
               }
+              __syncwarp();
+              const bool any = P.plane_mode ? (P.ksteps > 0) : (rows > 0 && P.ksteps > 0);
+              if (any) started |= (nkw == 3 ? 7u : 1u) << chain0;
             }
-            if (a == 0) umma_commit(xempty0 + 8 * xslot);  // plane t (+zoff) is not needed by later output planes
+            if (a == 0) {  // plane t (+zoff) is not needed by later output planes
+              if (elect_one()) umma_commit(xempty0 + 8 * xslot);
+              __syncwarp();
+            }
           }
-          umma_commit(yempty0 + 8 * yslot);
+          if (elect_one()) umma_commit(yempty0 + 8 * yslot);
+          __syncwarp();
           ++T;
         }
         // planes nz .. nz+xspan-2 of this item were only partially consumed: release them
         for (int a = 1; a < P.xspan; ++a) {
           const uint32_t q = Q0 + nz - 1 + a;
-          umma_commit(xempty0 + 8 * (q % P.R));
+          if (elect_one()) umma_commit(xempty0 + 8 * (q % P.R));
+          __syncwarp();
         }
         Q = Q0 + nz + P.xspan - 1;
       }
       if (cur_key >= 0) {
-        *s_started = started;
-        __threadfence_block();
-        umma_commit(accfull);
+        if (elect_one()) {
+          *s_started = started;
+          __threadfence_block();
+          umma_commit(accfull);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
