@@ -205,6 +205,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # exactly ONE line on stdout: everything else that writes to fd 1 (NCCL prints a version banner there) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -241,7 +245,12 @@ def main():
             graphed = True
         except Exception as e:  # noqa: BLE001 - fall back to the eager (still all-CUDA) step
             sys.stderr.write("[bench] CUDA-graph capture failed (%s: %s); running the eager step\n" % (type(e).__name__, e))
-            step = eager_step
+            step, graphed = eager_step, False
+        if world > 1:   # all ranks must run the same variant (a graphed rank and an eager rank would mismatch collectives)
+            flag = torch.tensor([1 if graphed else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                step, graphed = eager_step, False
 
     def barrier():
         torch.cuda.synchronize()
@@ -383,8 +392,13 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams,
             "inference": inference, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
+        barrier()
+        if graphed:   # tearing down NCCL while a captured graph still references its streams hangs: leave without it
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -28,7 +28,8 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        # thread_local: CUDA calls of other host threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._eager()
         torch.cuda.synchronize()
 
