@@ -355,13 +355,20 @@ def main():
     if not args.no_inference:
         model.eval()
         x1 = xd[:1].contiguous()
+        infer, inf_graphed = model, False
+        if use_graph:
+            try:
+                infer, inf_graphed = U.GraphedInference(model, x1), True
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("[bench] inference graph capture failed (%s); eager forward\n" % e)
+                infer = model
         with torch.no_grad():
             for _ in range(3):
-                model(x1)
+                infer(x1)
             barrier()
             e0.record()
             for _ in range(args.steps):
-                model(x1)
+                infer(x1)
             e1.record()
             barrier()
         ims = e0.elapsed_time(e1) / args.steps
@@ -370,7 +377,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ims = float(t.item())
         inference = {"value": world * 1e3 / ims, "unit": "volumes/s", "ms_per_volume": ims,
-                     "config": "batch 1 per GPU, 4x128^3, eval, bf16",
+                     "config": "batch 1 per GPU, 4x128^3, eval, bf16" + (", CUDA graph" if inf_graphed else ""),
                      "conv_tflops": FWD_FLOP_PER_VOXEL * SIZE ** 3 / (ims * 1e-3) / 1e12}
         model.train()
 

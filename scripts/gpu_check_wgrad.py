@@ -47,6 +47,8 @@ if __name__ == "__main__":
         ok &= case(1, 2, 8, 16, 128, 96)
         ok &= case(2, 1, 4, 16, 32, 32)
         ok &= case(1, 9, 33, 128, 16, 16)
+    if which == "one":
+        ok &= case(2, 128, 128, 128, 32, 32, iters=3)
     if which in ("all", "perf"):
         ok &= case(2, 128, 128, 128, 32, 32, iters=3)
         ok &= case(2, 128, 128, 128, 64, 32, iters=3)

@@ -226,6 +226,90 @@ static void run_lean(int issuers, int grid) {
   cudaFree(d);
 }
 
+
+// MN-major variant (what conv_wg2.cu issues): A = 4 groups of 32 channels shifted by 1 row each (LBO = 1 row), B = N/32
+// groups shifted by `rowpitch` rows, SWIZZLE_64B rows of 64 bytes, K = 16 consecutive rows.
+template <int N>
+__global__ void __launch_bounds__(128, 1) lean_mn_kernel(const LP P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  uint32_t* w = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) { uint32_t h = (uint32_t)i * 2654435761u; w[i] = 0x3C003C00u | (h & 0x007F007Fu); }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  if (warp < P.issuers) {
+    constexpr uint32_t RB = 64, rb16 = 4;
+    const uint32_t sA16 = smem_u32(smem) >> 4;                 // dY-like tile: rows of 64 B
+    const uint32_t sB16 = sA16 + (40 * 1024 >> 4);             // X-like planes
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t hi = ((uint64_t)(((8u * RB) >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)4 << 61);
+    const uint32_t lboA = (RB >> 4) << 16;
+    const uint32_t lboB = (((uint32_t)P.rowpitch * RB) >> 4) << 16;
+    const uint32_t d0 = tmem + (uint32_t)(warp * 128);
+    long long t0 = clock64();
+    for (int blk = 0; blk < P.blocks; ++blk) {
+      const uint32_t ab = (sA16 + (uint32_t)((blk & 1) * 130) * rb16) | lboA;
+      const uint32_t bb = (sB16 + (uint32_t)((blk & 1) * P.rowpitch) * rb16) | lboB;
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
+            mma_ss(d0 + kd * 0, hi | (ab + j * 16 * rb16), hi | (bb + kd * (40 * 1024 >> 4) + j * 16 * rb16), idesc, (blk | j | kd) ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+    }
+    const uint32_t bbar = smem_u32(&bars[warp]);
+    if (elect_one())
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bbar) : "memory");
+    __syncwarp();
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bbar), "r"(0) : "memory");
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) P.out[blockIdx.x * 4 + warp] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+template <int N>
+static void run_lean_mn(int rowpitch, int grid) {
+  const int blocks = 800;
+  long long* d;
+  CHECK(cudaMalloc(&d, sizeof(long long) * grid * 4));
+  CHECK(cudaMemset(d, 0, sizeof(long long) * grid * 4));
+  LP P{blocks, 1, rowpitch, d};
+  CHECK(cudaFuncSetAttribute(lean_mn_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+  lean_mn_kernel<N><<<grid, 128, 201 * 1024>>>(P);
+  CHECK(cudaDeviceSynchronize());
+  lean_mn_kernel<N><<<grid, 128, 201 * 1024>>>(P);
+  CHECK(cudaDeviceSynchronize());
+  std::vector<long long> h(grid * 4);
+  CHECK(cudaMemcpy(h.data(), d, sizeof(long long) * grid * 4, cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  for (auto v : h) mx = std::max(mx, v);
+  const double clk = (double)mx / ((double)blocks * 24);
+  printf("LEAN MN-major SW64 N=%3d (A groups 1 row apart, B groups %d rows apart): clk/MMA %.1f (K-major model: %.0f)\n", N, rowpitch, clk,
+         std::max(N / 2.0, (4096.0 + 32.0 * N) / 128.0));
+  cudaFree(d);
+}
+
 static void run(const char* name, RP P, int grid) {
   long long* d;
   CHECK(cudaMalloc(&d, sizeof(long long) * grid));
@@ -254,6 +338,13 @@ static void run(const char* name, RP P, int grid) {
 
 int main(int argc, char** argv) {
   const bool ts = argc > 1 && !strcmp(argv[1], "ts");
+  if (argc > 1 && !strcmp(argv[1], "mn")) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    run_lean_mn<96>(128, sms); run_lean_mn<96>(130, sms); run_lean_mn<96>(64, sms); run_lean_mn<48>(128, sms);
+    run_lean_mn<32>(128, sms); run_lean_mn<64>(128, sms); run_lean_mn<128>(128, sms);
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "lean")) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);

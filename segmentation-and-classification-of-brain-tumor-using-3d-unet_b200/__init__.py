@@ -4,4 +4,4 @@ from .modules import UNet3D, DoubleConv3D, AttentionGate3D  # noqa: F401
 from .losses import (CombinedLoss3D, TverskyLoss3D, DeepSupervisionLoss3D, CombinedLoss, DiceLoss,  # noqa: F401
                      FocalLoss)
 from .metrics import calculate_dice_score, dice_score, confusion_matrix, segment, tumor_volumes  # noqa: F401
-from .graph import GraphedTrainStep  # noqa: F401
+from .graph import GraphedTrainStep, GraphedInference  # noqa: F401

@@ -50,3 +50,30 @@ class GraphedTrainStep:
             self.y.copy_(y, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+class GraphedInference:
+    """Eval-mode forward (main.py:390-393 / train_model.py:216-217 call sites) captured once and replayed:
+        infer = GraphedInference(model, volume);  logits = infer(volume)   # static output buffer, fp32 NCDHW"""
+
+    def __init__(self, model, example_x, warmup=3):
+        assert not model.training, "GraphedInference captures the eval-mode forward"
+        self.model = model
+        self.x = example_x.detach().clone()
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self.model(self.x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.out = self.model(self.x)
+        torch.cuda.synchronize()
+
+    def __call__(self, x):
+        if x is not self.x:
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out
