@@ -344,7 +344,10 @@ def main():
         roof = {"kernel": "zs_kernel / igemm_kernel (3x3x3 conv fprop + dgrad, tcgen05 implicit GEMM)", "bound": "tensor",
                 "achieved": ach,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
+                # dram__bytes_read+write of the representative launch (zs_kernel<32,32>, 32->32 @2x128^3, ncu --set full,
+                # profiles/ncu_r1_zs_32_32_final.txt) vs 536.9 MB algorithmic (one read + one write of a 268 MB tensor)
+                "traffic": 674.1e6, "traffic_kernel": "zs_kernel<32,32> 32->32 3x3x3 @2x128^3: 674 MB DRAM vs 537 MB algorithmic",
+                "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
                 "avg_launch_ms": tms / max(cnt, 1), "algorithmic_gflop_per_launch": fl / max(cnt, 1) / 1e9,
                 "share_of_step": tms / ms_prof,
                 "measured_in": "eager pass of the same step inside bench.py (CUDA events around every launch), %.2f ms/step"
