@@ -78,7 +78,7 @@ def conv_case(N, D, H, W, Cin, Cout, ks, groups=8, bias=False, iters=0):
     return ok
 
 
-def convT_case(N, D, H, W, Cin, Cout):
+def convT_case(N, D, H, W, Cin, Cout, iters=0):
     torch.manual_seed(1)
     x = torch.randn(N, D, H, W, Cin, device=dev).to(torch.bfloat16)
     w = (torch.randn(Cin, Cout, 2, 2, 2, device=dev) / Cin ** 0.5).to(torch.bfloat16).float()
@@ -92,7 +92,22 @@ def convT_case(N, D, H, W, Cin, Cout):
     ref = F.conv_transpose3d(x.float().permute(0, 4, 1, 2, 3), w, b, stride=2).permute(0, 2, 3, 4, 1)
     diff = (y.float() - ref).abs().max().item()
     ok = diff <= 2e-2 * max(ref.abs().max().item(), 1.0)
-    print("convT N%d %dx%dx%d Cin%d Cout%d: maxdiff %.4g %s" % (N, D, H, W, Cin, Cout, diff, "OK" if ok else "FAIL"), flush=True)
+    msg = "convT N%d %dx%dx%d Cin%d Cout%d: maxdiff %.4g %s" % (N, D, H, W, Cin, Cout, diff, "OK" if ok else "FAIL")
+    if iters:
+        def run():
+            _lib.check(L.b3d_convT2_fprop(_lib.ptr(x), c_ll(Cin), _lib.ptr(wp), _lib.ptr(b), _lib.ptr(y), c_ll(Cout), c_int(N), c_int(D),
+                                          c_int(H), c_int(W), c_int(Cin), c_int(Cout), _lib.ptr(err), _lib.stream_ptr()))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        msg += "  %.3f ms" % (e0.elapsed_time(e1) / iters)
+    print(msg, flush=True)
     # dgrad: dx = conv_transpose^T(dy)
     dy = torch.randn(N, 2 * D, 2 * H, 2 * W, Cout, device=dev).to(torch.bfloat16)
     rows = ru(Cin, 16)
@@ -139,6 +154,12 @@ if __name__ == "__main__":
         allok &= conv_case(2, 2, 16, 16, 16, 64, 3)
     if which == "one":  # a single launch of the dominant layer shape, for ncu
         allok &= conv_case(2, 128, 128, 128, 32, 32, 3)
+    if which == "convT":
+        allok &= convT_case(1, 4, 4, 4, 32, 16)
+        allok &= convT_case(2, 8, 8, 8, 64, 32)
+        allok &= convT_case(1, 8, 16, 16, 128, 64)
+        allok &= convT_case(2, 64, 64, 64, 64, 32, iters=5)
+        allok &= convT_case(2, 32, 32, 32, 128, 64, iters=5)
     if which == "pw":
         allok &= conv_case(2, 128, 128, 128, 16, 32, 1, iters=5)
     if which == "pw64":

@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       const int cmax = (P.mode == 2 ? P.ps_cout : P.Cout);
       int t8 = 0, ch_base = n0;
       if (P.mode == 2) { t8 = n0 / P.ps_cout; ch_base = n0 - t8 * P.ps_cout; }
-      const bool full = (ch_base + BN <= cmax);   // every column of this n-block is a real channel
+      // every column of this n-block is a real channel (pixel shuffle: n-blocks cover whole taps of ps_cout % 16 == 0 channels)
+      const bool full = (P.mode == 2) ? (P.ps_cout % 16 == 0) : (ch_base + BN <= cmax);
       // specialised bodies: one (mode, statistics granule) combination runs, without per-element predicates
       auto body = [&](auto MODE_c, auto GRAN_c, auto FULL_c) {
         constexpr int MODE = decltype(MODE_c)::value, GRAN = decltype(GRAN_c)::value;
@@ -254,13 +255,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           const int py = pr / P.BW, px = pr - py * P.BW;
           const int z = tz * P.TD + pz, y = ty * P.TH + py, x = tx * P.TW + px;
           const bool valid = (pz < P.TD) && (py < P.TH) && (px < P.TW) && (z < P.D) && (y < P.H) && (x < P.W);
-          long long vox;
-          if (MODE == 2) {
-            const int oz = 2 * z + (t8 >> 2), oy = 2 * y + ((t8 >> 1) & 1), ox = 2 * x + (t8 & 1);
-            vox = (((long long)n * (2 * P.D) + oz) * (2 * P.H) + oy) * (2 * P.W) + ox;
-          } else {
-            vox = (((long long)n * P.D + z) * P.H + y) * P.W + x;
-          }
+          long long vox = (((long long)n * P.D + z) * P.H + y) * P.W + x;   // MODE 2: recomputed per 32-column chunk (tap)
           const uint32_t trow = tmem_base + a * P.acc_stride + mb * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
           for (int j0 = 0; j0 < BN; j0 += 32) {
@@ -270,7 +265,13 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
             if (NC == 32) tmem_ld16(trow + j0 + 16, r + 16);
             tmem_ld_wait();
             float v[NC];
-            const int c0 = ch_base + j0;
+            int c0 = ch_base + j0;
+            if (MODE == 2) {   // pixel shuffle: this chunk of columns belongs to tap t8j of the 2x2x2 up-sampling
+              const int t8j = (n0 + j0) / P.ps_cout;
+              c0 = (n0 + j0) - t8j * P.ps_cout;
+              const int oz = 2 * z + (t8j >> 2), oy = 2 * y + ((t8j >> 1) & 1), ox = 2 * x + (t8j & 1);
+              vox = (((long long)n * (2 * P.D) + oz) * (2 * P.H) + oy) * (2 * P.W) + ox;
+            }
 #pragma unroll
             for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
             if (P.bias != nullptr) {
@@ -533,7 +534,11 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
               if (BN > CoutPad && BN != 16) continue;
               if (BN > CoutPad) continue;
               if (CoutPad % BN) continue;
-              if (mode == 2 && (BN > CoutPad / 8 || (CoutPad / 8) % BN)) continue;  // pixel shuffle: n-block inside one tap
+              if (mode == 2) {  // pixel shuffle: an n-block lies inside one tap, or covers whole taps of >= 32 channels
+                const int ps = CoutPad / 8;
+                const bool inside = (BN <= ps && ps % BN == 0), whole = (BN % ps == 0 && ps % 32 == 0);
+                if (!inside && !whole) continue;
+              }
               if (chan_per_map % KC) continue;
               if (env_kc && KC != env_kc) continue;
               if (env_bn && BN != env_bn) continue;

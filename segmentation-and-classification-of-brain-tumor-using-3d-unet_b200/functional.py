@@ -10,23 +10,27 @@ import torch
 
 from . import ops
 
-_PACK_CACHE = {}
-
-
 def packed(param, mode):
-    """bf16 tcgen05-ready copy of a conv weight, cached until the parameter is modified in place (optimizer step,
-    load_state_dict, .to(device)): keyed on the tensor's version counter and storage address."""
-    key = (id(param), mode)
-    hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == param._version and hit[1] == param.data_ptr():
-        return hit[2], hit[3], hit[4]
+    """bf16 tcgen05-ready copy of a conv weight, cached ON the parameter object until it is modified in place (optimizer
+    step, load_state_dict, .to(device)): validated by the tensor's version counter and storage address.  (A global cache
+    keyed by id(param) is wrong: a new model can reuse the id, the version and — through the caching allocator — even the
+    address of a freed parameter, and would silently get the old model's packed weights.)"""
+    cache = param.__dict__.setdefault("_b3d_pack", {})
+    hit = cache.get(mode)
+    if hit is not None and hit[0] == (param._version, param.data_ptr(), _PACK_EPOCH[0]):
+        return hit[1], hit[2], hit[3]
     wp, kp, rows = ops.pack_weight(param, mode)
-    _PACK_CACHE[key] = (param._version, param.data_ptr(), wp, kp, rows)
+    cache[mode] = ((param._version, param.data_ptr(), _PACK_EPOCH[0]), wp, kp, rows)
     return wp, kp, rows
 
 
+_PACK_EPOCH = [0]
+
+
 def clear_pack_cache():
-    _PACK_CACHE.clear()
+    """Invalidate every cached packed weight.  A replayed CUDA graph (graph.py) updates parameters without touching their
+    Python version counters, so GraphedTrainStep calls this after every replay."""
+    _PACK_EPOCH[0] += 1
 
 
 def act_padded(n, d, h, w, c, device):

@@ -13,6 +13,8 @@ host synchronisation, which is what makes it capturable.  The optimizer must be 
 """
 import torch
 
+from . import functional
+
 
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3):
@@ -49,17 +51,51 @@ class GraphedTrainStep:
         if y is not self.y:
             self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        functional.clear_pack_cache()   # parameters changed behind the version counters: eager calls must re-pack
+        return self.loss
+
+    # -- input pipelining: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes ----------
+    def prefetch(self, x_host, y_host):
+        """Start copying the NEXT batch (pinned host tensors) into staging buffers on a side stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._sx, self._sy = torch.empty_like(self.x), torch.empty_like(self.y)
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)       # the previous staged batch has been moved into the static buffers
+        with torch.cuda.stream(self._copy_stream):
+            self._sx.copy_(x_host, non_blocking=True)
+            self._sy.copy_(y_host, non_blocking=True)
+            self._staged.record()
+
+    def step_prefetched(self):
+        """Run one step on the batch handed to the last prefetch() (device-to-device move, then replay)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self.x.copy_(self._sx, non_blocking=True)
+        self.y.copy_(self._sy, non_blocking=True)
+        self._consumed.record()
+        self.graph.replay()
+        functional.clear_pack_cache()
         return self.loss
 
 
 class GraphedInference:
     """Eval-mode forward (main.py:390-393 / train_model.py:216-217 call sites) captured once and replayed:
-        infer = GraphedInference(model, volume);  logits = infer(volume)   # static output buffer, fp32 NCDHW"""
+        infer = GraphedInference(model, volume);  logits = infer(volume)   # static output buffer, fp32 NCDHW
+    The bf16 packed weights are frozen at capture time (serving); call `refresh()` after the parameters changed."""
 
     def __init__(self, model, example_x, warmup=3):
         assert not model.training, "GraphedInference captures the eval-mode forward"
         self.model = model
         self.x = example_x.detach().clone()
+        self._warmup = warmup
+        self.refresh()
+
+    def refresh(self):
+        warmup = self._warmup
+        functional.clear_pack_cache()
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

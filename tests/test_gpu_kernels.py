@@ -310,3 +310,67 @@ def test_convT2_wgrad(n, s, cin, cout):
     wt = torch.zeros(cin, cout, 2, 2, 2, device=DEV, requires_grad=True)
     F.conv_transpose3d(_ncdhw(x), wt, None, stride=2).backward(_ncdhw(dy))
     assert (dw - wt.grad).abs().max().item() <= 2e-3 * wt.grad.abs().max().item() + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# round-1 kernel set: shapes that select each conv code path (conv_zs.cu / conv_igemm.cu variants, conv_wg2.cu)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,h,w,cin,cout,bias,groups", [
+    (1, 8, 16, 128, 32, 32, False, 8),    # zs: COUT 32, full-width planes, several columns per CTA
+    (2, 16, 8, 128, 64, 32, True, 8),     # zs: KC 64
+    (1, 8, 12, 64, 16, 16, False, 16),    # zs: COUT 16 (N = 48), per-channel statistics, ragged H
+    (2, 5, 9, 40, 32, 64, False, 8),      # zs: COUT 64 (ring of 8 slots), odd extents, ring wrap
+    (1, 6, 16, 24, 128, 64, False, 8),    # zs: two K chunks, output-channel blocks of 16 (weights resident per block)
+    (1, 7, 20, 16, 64, 128, False, 8),    # zs: 4 channel blocks of 32 -> weight reload between segments
+    (2, 3, 64, 64, 16, 32, False, 8),     # zs: more CTAs than columns -> segments of 1-2 planes
+    (2, 8, 16, 16, 128, 128, True, 8),    # igemm patch tiles, BN 128
+    (2, 4, 4, 4, 256, 512, False, 8),     # igemm linear tiles + split-K slices
+    (1, 2, 2, 2, 128, 256, False, 8),     # igemm, 8 voxels
+])
+def test_conv3_paths(n, d, h, w, cin, cout, bias, groups):
+    x = _bf(n, d, h, w, cin, seed=41)
+    wt = (_bf(cout, cin, 3, 3, 3, seed=42).float() / (cin * 27) ** 0.5).to(BF).float()
+    b = torch.randn(cout, device=DEV) if bias else None
+    wp, kp, rows = ops.pack_weight(wt, ops.PACK_FPROP)
+    y, st = ops.conv_fprop(x, wp, rows, cout, 3, bias=b, groups=groups)
+    ref = _ndhwc(F.conv3d(_ncdhw(x), wt, b, padding=1))
+    _close_bf16(y, ref)
+    rs = _stats(ref, groups)
+    assert ((st - rs).abs() / (rs.abs() + 1.0)).max().item() < 2e-3
+    # dgrad of the same layer = the same kernels on flipped / transposed packed weights
+    dy = _bf(n, d, h, w, cout, seed=43)
+    wd, _, rowsd = ops.pack_weight(wt, ops.PACK_DGRAD)
+    dx, _ = ops.conv_fprop(dy, wd, rowsd, cin, 3)
+    _close_bf16(dx, _ndhwc(F.conv_transpose3d(_ncdhw(dy), wt, padding=1)))
+
+
+@pytest.mark.parametrize("n,s,cin,cout", [(1, 8, 128, 64), (2, 16, 64, 32), (1, 16, 32, 16)])
+def test_convT2_fprop_multi_tap_blocks(n, s, cin, cout):
+    """ConvTranspose n-blocks that span several 2x2x2 taps (pixel-shuffle target recomputed per 32-column chunk)."""
+    x = _bf(n, s, s, s, cin, seed=44)
+    w = (_bf(cin, cout, 2, 2, 2, seed=45).float() / cin ** 0.5).to(BF).float()
+    b = torch.randn(cout, device=DEV)
+    wp, kp, rows = ops.pack_weight(w, ops.PACK_CONVT_FPROP)
+    y = ops.convT2_fprop(x, wp, b, cout)
+    _close_bf16(y, _ndhwc(F.conv_transpose3d(_ncdhw(x), w, b, stride=2)))
+
+
+@pytest.mark.parametrize("n,d,h,w,cin,cout", [
+    (1, 4, 8, 32, 32, 32),      # wg2 <32,32>, one key
+    (2, 5, 7, 48, 32, 32),      # ragged H, W = 3 x 16
+    (2, 6, 9, 64, 32, 16),      # 16-channel dY blocks (8 descriptor groups on M)
+    (1, 3, 16, 16, 16, 32),     # 16-channel X blocks (N = 48)
+    (1, 8, 16, 32, 64, 64),     # 4 keys
+    (1, 2, 8, 16, 128, 96),     # 12 keys, more keys than planes per CTA
+    (2, 1, 4, 16, 32, 32),      # a single plane: the kd = 0 / 2 chains never start
+    (1, 9, 33, 128, 16, 16),    # full-width rows, ragged H
+])
+def test_conv_wgrad_mn_major(n, d, h, w, cin, cout):
+    x = _bf(n, d, h, w, cin, seed=46)
+    dy = _bf(n, d, h, w, cout, seed=47)
+    dw = ops.conv_wgrad(x, dy, cin, cout, 3)
+    wt = torch.zeros(cout, cin, 3, 3, 3, device=DEV, requires_grad=True)
+    F.conv3d(_ncdhw(x), wt, None, padding=1).backward(_ncdhw(dy))
+    ref = wt.grad
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, "max err %g vs scale %g" % (err, ref.abs().max().item())

@@ -264,3 +264,56 @@ def test_segment_and_volumes_bit_exact():
     vols = U.tumor_volumes(mask[0])
     tumour, per_class, per_slice = O.voxel_counts(mask[0].cpu())
     assert vols == {"tumor_voxels": tumour, "class_voxels": per_class, "slice_voxels": per_slice}
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (zero_grad + forward + DS loss + backward + AdamW as one CUDA graph) follows the eager step."""
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(4, 4, feats, seed=5)
+    x, y = O.make_inputs(2, 32, 32, 32, seed=5)
+    xd, yd = x.to(DEV), y.to(DEV)
+    losses = {}
+    for mode in ("eager", "graph"):
+        model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), sd).train()
+        crit = U.DeepSupervisionLoss3D()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=True)
+        out = []
+        if mode == "graph":
+            # the capture protocol runs 3 warm-up optimizer steps: undo them so that both runs start from the same weights
+            step = U.GraphedTrainStep(model, crit, opt, xd, yd, warmup=1)
+            model.load_state_dict(sd)
+            opt.state.clear()
+            for _ in range(3):
+                out.append(float(step(xd, yd)))
+        else:
+            for _ in range(3):
+                opt.zero_grad(set_to_none=True)
+                loss = crit(model(xd), yd)
+                loss.backward()
+                opt.step()
+                out.append(float(loss))
+        losses[mode] = out
+    e, g = losses["eager"], losses["graph"]
+    assert abs(e[0] - g[0]) <= 2e-3 * abs(e[0]), (e, g)          # same weights, same batch: first losses agree (bf16 jitter)
+    assert e[2] < e[0] and g[2] < g[0], (e, g)                    # both actually train
+    assert abs(e[2] - g[2]) <= 5e-2 * abs(e[2]), (e, g)
+
+
+def test_packed_weight_cache_is_per_parameter():
+    """Regression: the packed-weight cache used to be keyed by id(param); a second model that re-used the id, version and
+    address of a freed parameter silently ran with the first model's weights."""
+    import gc
+    from unet3d_b200 import functional
+    feats = (16, 32, 64, 128, 256)
+    x, _ = O.make_inputs(1, 32, 32, 32, seed=7)
+    xd = x.to(DEV)
+    outs = []
+    for seed in (1, 2, 1, 2):
+        model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), O.make_state_dict(4, 4, feats, seed=seed)).eval()
+        with torch.no_grad():
+            outs.append(model(xd).clone())
+        del model
+        gc.collect()
+    assert _rel_l2(outs[2], outs[0]) < 3e-2 and _rel_l2(outs[3], outs[1]) < 3e-2     # same weights -> same logits
+    assert _rel_l2(outs[1], outs[0]) > 0.3                                            # different weights -> different logits
+    functional.clear_pack_cache()
