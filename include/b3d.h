@@ -34,6 +34,11 @@ int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void
 int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
                    int N, int D, int H, int W, int Cin, int Cout, int ks, double* stats, int groups, int stats_batch,
                    void* ws, size_t ws_bytes, int* err_flag, void* stream);
+/* same, with a fused  y = conv(x) + addend  (1x1x1 only; addend may alias y).  Replaces the separate accumulation autograd
+ * performs when two branches feed the same tensor (residual 1x1 branch main.py:229-231,240; gate projections main.py:282-283) */
+int b3d_conv_fprop_add(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, const void* addend,
+                       long long ld_add, void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int ks,
+                       double* stats, int groups, int stats_batch, void* ws, size_t ws_bytes, int* err_flag, void* stream);
 /* nn.ConvTranspose3d(2f,f,k=2,s=2) main.py:121,183 forward / data gradient */
 int b3d_convT2_fprop(const void* x, long long ldx, const void* wpack, const float* bias, void* y, long long ldy, int N,
                      int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);

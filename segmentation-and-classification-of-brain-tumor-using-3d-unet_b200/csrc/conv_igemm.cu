@@ -49,6 +49,7 @@ struct alignas(64) IgParams {
   bf16* out; long long ld_out;
   int ps_cout;           // pixel shuffle: channels per tap
   const float* bias;
+  const bf16* addend; long long ld_add;   // mode 0: out = conv + addend (gradient accumulation of two branches), may alias out
   float* out_f32; long long ld_f32; long long slice_f32;  // split-K partials: [ksplit][V][ld_f32]
   double* stats; int cpg; int stats_groups; int stats_batch;
   int* err;
@@ -284,6 +285,18 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
               } else {
 #pragma unroll
                 for (int j = 0; j < NC; ++j) if (c0 + j < cmax) v[j] += __ldg(P.bias + c0 + j);
+              }
+            }
+            if (MODE == 0 && P.addend != nullptr && valid) {   // fused branch-gradient add (replaces a separate add pass)
+              const bf16* ap = P.addend + vox * P.ld_add + c0;
+#pragma unroll
+              for (int h = 0; h < NC / 8; ++h) {
+                if (FULL || c0 + 8 * h + 8 <= cmax) {
+                  float t8v[8];
+                  unpack8(ldg16(ap + 8 * h), t8v);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[8 * h + j] += t8v[j];
+                }
               }
             }
             if (valid) {
@@ -608,7 +621,7 @@ static int ig_launch(const IgParams& P, size_t smem, int grid, cudaStream_t stre
 static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf16* wpack, int w_rows, int ks,
                      int N, int D, int H, int W, int Cout, int mode, bf16* out, long long ld_out, int ps_cout,
                      const float* bias, double* stats, int cpg, int stats_groups, int stats_batch, float* ws,
-                     size_t ws_bytes, int* err_flag, cudaStream_t stream) {
+                     size_t ws_bytes, int* err_flag, cudaStream_t stream, const bf16* addend = nullptr, long long ld_add = 0) {
   const int halo = ks / 2, KD = ks, KHW = ks * ks;
   const int num_sms = b3d_num_sms();
   const int CoutPad = w_rows;  // rows in the packed weight tensor (multiple of 16)
@@ -622,7 +635,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
     stat_gran = cpg >= 16 ? 16 : (cpg >= 4 ? 4 : 1);
   }
   int max_split = 1;  // split-K partials are plain stores into per-split workspace slices [ksplit][V][Cout] fp32
-  if (mode == 0 && ws != nullptr && Cout % 8 == 0) max_split = (int)std::min<size_t>(64, ws_bytes / ((size_t)N * D * H * W * Cout * 4));
+  if (mode == 0 && ws != nullptr && Cout % 8 == 0 && addend == nullptr) max_split = (int)std::min<size_t>(64, ws_bytes / ((size_t)N * D * H * W * Cout * 4));
   IgemmPlan pl = plan_igemm(N, D, H, W, chan_per_map, nmaps, CoutPad, ks, mode, num_sms, max_split, stat_gran);
   if (!pl.ok) {
     b3d_set_error("igemm: no tile plan for N=%d D=%d H=%d W=%d K=%dx%d Cout=%d ks=%d", N, D, H, W, nmaps, chan_per_map,
@@ -661,7 +674,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   P.a_tx = (uint32_t)(box_vox * RB); P.w_tx = (uint32_t)(KHW * BN * RB);
   P.w_off = (P.a_tx + 1023u) / 1024u * 1024u;
   P.stage_bytes = P.w_off + (P.w_tx + 1023u) / 1024u * 1024u;
-  P.mode = mode; P.out = out; P.ld_out = ld_out; P.ps_cout = ps_cout; P.bias = bias;
+  P.mode = mode; P.out = out; P.ld_out = ld_out; P.ps_cout = ps_cout; P.bias = bias; P.addend = addend; P.ld_add = ld_add;
   P.stats = stats; P.cpg = cpg > 0 ? cpg : 16; P.stats_groups = stats_groups; P.stats_batch = stats_batch;
   P.err = err_flag;
 
@@ -738,9 +751,9 @@ int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void
 // Stride-1 "same" convolution, ks in {1,3}.  x: NDHWC bf16 with voxel pitch ldx (elements), Cin channels used (mult of 16).
 // wpack: packed [Cin/8][ks^3][rows][8] (rows = roundup16(Cout)).  y: NDHWC bf16 pitch ldy.  stats: optional double
 // [N or 1][groups][2] accumulated (+=) with sum / sum of squares of the (bias-added, fp32) outputs.
-int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
-                   int N, int D, int H, int W, int Cin, int Cout, int ks, double* stats, int groups, int stats_batch,
-                   void* ws, size_t ws_bytes, int* err_flag, void* stream) {
+int b3d_conv_fprop_add(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, const void* addend,
+                       long long ld_add, void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int ks,
+                       double* stats, int groups, int stats_batch, void* ws, size_t ws_bytes, int* err_flag, void* stream) {
   B3D_REQUIRE(ks == 1 || ks == 3, "conv_fprop: ks must be 1 or 3");
   B3D_REQUIRE(Cin % 16 == 0, "conv_fprop: Cin (%d) must be a multiple of 16 (pad the activation)", Cin);
   B3D_REQUIRE(Cout % 8 == 0, "conv_fprop: Cout (%d) must be a multiple of 8", Cout);
@@ -759,6 +772,7 @@ int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, 
   v.base = x; v.C = Cin; v.W = w; v.H = h; v.D = d; v.N = n;
   v.sW = ldx * 2; v.sH = v.sW * w; v.sD = v.sH * h; v.sN = v.sD * d;
   const int cpg = (stats && groups > 0) ? Cout / groups : 0;
+  if (addend != nullptr) B3D_REQUIRE(ks == 1 && ld_add % 8 == 0, "conv_fprop_add: the fused addend is implemented for 1x1x1 convolutions");
   if (ks == 3) {  // large planes, few output channels: z-marching kd-stacked kernel (conv_zs.cu)
     const int rc = b3d_try_zs(x, ldx, wpack, w_rows, bias, y, ldy, N, D, H, W, Cin, Cout, stats, cpg, groups, stats_batch,
                               err_flag, (cudaStream_t)stream);
@@ -777,7 +791,14 @@ int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, 
     v.sW = ldx * 2; v.sH = v.sW * w; v.sD = v.sH * h; v.sN = v.sD * d;
   }
   return run_igemm(&v, 1, Cin, (const bf16*)wpack, w_rows, ks, n, d, h, w, Cout, 0, (bf16*)y, ldy, 0, bias, stats, cpg,
-                   groups, stats_batch, (float*)ws, ws_bytes, err_flag, (cudaStream_t)stream);
+                   groups, stats_batch, (float*)ws, ws_bytes, err_flag, (cudaStream_t)stream, (const bf16*)addend, ld_add);
+}
+
+int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
+                   int N, int D, int H, int W, int Cin, int Cout, int ks, double* stats, int groups, int stats_batch,
+                   void* ws, size_t ws_bytes, int* err_flag, void* stream) {
+  return b3d_conv_fprop_add(x, ldx, wpack, w_rows, bias, nullptr, 0, y, ldy, N, D, H, W, Cin, Cout, ks, stats, groups, stats_batch,
+                            ws, ws_bytes, err_flag, stream);
 }
 
 // ConvTranspose3d(k=2,s=2) forward: x [N,D,H,W,Cin] -> y [N,2D,2H,2W,Cout] (pitch ldy), bias added.

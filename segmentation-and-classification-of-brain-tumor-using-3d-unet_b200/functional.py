@@ -101,8 +101,7 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
         grads[pre + "residual.0.weight"] = ops.conv_wgrad(x, dr, cin_real, cout, 1)
         if need_dx:
             wrd, _, rowsrd = packed(p[pre + "residual.0.weight"], ops.PACK_DGRAD)
-            dxr, _ = ops.conv_fprop(dr, wrd, rowsrd, x.shape[-1], 1)
-            ops.add_bf16(dx, dxr, out=dx)
+            ops.conv_fprop(dr, wrd, rowsrd, x.shape[-1], 1, out=dx, add=dx)   # dx += residual-branch gradient, fused
     elif need_dx:
         ops.add_bf16(dx, dout, out=dx)
     return dx, grads
@@ -135,8 +134,8 @@ def gate_fwd(g, x, p, pre, out, need_bwd):
     return out, saved
 
 
-def gate_bwd(saved, dout, p, pre):
-    """Returns (dg, dx, grads)."""
+def gate_bwd(saved, dout, p, pre, dg_add=None):
+    """Returns (dg [+ dg_add], dx, grads)."""
     g, x, g1r, x1r, st_g, st_x, psi_raw, st_psi, ca, z, mean = saved
     n, d, h, w, c = x.shape
     f = g1r.shape[-1]
@@ -172,9 +171,9 @@ def gate_bwd(saved, dout, p, pre):
     grads[pre + "W_x.0.bias"] = bias_grad(dx1r)
     wgd, _, rowsgd = packed(p[pre + "W_g.0.weight"], ops.PACK_DGRAD)
     wxd, _, rowsxd = packed(p[pre + "W_x.0.weight"], ops.PACK_DGRAD)
-    dg, _ = ops.conv_fprop(dg1r_full, wgd, rowsgd, c, 1)
-    dxg, _ = ops.conv_fprop(dx1r_full, wxd, rowsxd, c, 1)
-    ops.add_bf16(dx, dxg, out=dx)
+    # dg is only ever added to the gradient of the up-sampled half of the concat buffer: fuse that add (dg_add)
+    dg, _ = ops.conv_fprop(dg1r_full, wgd, rowsgd, c, 1, add=dg_add)
+    ops.conv_fprop(dx1r_full, wxd, rowsxd, c, 1, out=dx, add=dx)                 # dx += W_x-branch gradient, fused
     ops.add_channel_const(dx, xadd)
     return dg, dx, grads
 
@@ -198,9 +197,7 @@ def up_gate_fwd(x_low, skip, p, idx, need_bwd):
 def up_gate_bwd(saved, dcat, p, idx):
     """Returns (dx_low, dskip, grads)."""
     x_low, gsaved, cin, c = saved
-    dg, dskip, grads = gate_bwd(gsaved, dcat[..., :c], p, "ups.%d." % (idx + 1))
-    du = ops.add_bf16(dcat[..., c:], dg)
-    del dg
+    du, dskip, grads = gate_bwd(gsaved, dcat[..., :c], p, "ups.%d." % (idx + 1), dg_add=dcat[..., c:])
     wt = p["ups.%d.weight" % idx]
     grads["ups.%d.weight" % idx] = ops.convT2_wgrad(x_low, du, cin, c)
     grads["ups.%d.bias" % idx] = bias_grad(du)

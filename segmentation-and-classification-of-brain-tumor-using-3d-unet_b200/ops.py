@@ -96,9 +96,10 @@ def pack_weight(w, mode):
 # ---------------------------------------------------------------------------------------------------------------
 # tcgen05 convolutions
 # ---------------------------------------------------------------------------------------------------------------
-def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=False, out=None, cin=None):
-    """y = conv(x) (+bias); optional GroupNorm (per sample) or BatchNorm (stats_batch) partial sums of y.
-    `cin`: number of leading channels of x to contract over (multiple of 16; defaults to all)."""
+def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=False, out=None, cin=None, add=None):
+    """y = conv(x) (+bias) (+add); optional GroupNorm (per sample) or BatchNorm (stats_batch) partial sums of y.
+    `cin`: number of leading channels of x to contract over (multiple of 16; defaults to all).
+    `add`: NDHWC bf16 tensor summed into the result in the epilogue (1x1x1 only; may be `out` itself)."""
     n, d, h, w, c = x.shape
     cin = c if cin is None else cin
     dev = x.device
@@ -109,10 +110,11 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
         stats = torch.zeros((1 if stats_batch else n, groups, 2), dtype=torch.float64, device=dev)
     # split-K workspace: up to 16 fp32 partial slices [split][V][Cout]; only small (deep-level) problems ever split
     one = n * d * h * w * cout * 4
-    ws_bytes = one * 16 if one * 16 <= (1 << 26) else 0
+    ws_bytes = one * 16 if (one * 16 <= (1 << 26) and add is None) else 0
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
     with _prof("igemm", 2.0 * n * d * h * w * cin * cout * ks ** 3, "conv%d %dx%dx%dx%d %d->%d" % (ks, n, d, h, w, cin, cout)):
-        check(_L().b3d_conv_fprop(ptr(x), c_ll(ld(x)), ptr(wpack), c_int(w_rows), ptr(bias), ptr(out), c_ll(ld(out)),
+        check(_L().b3d_conv_fprop_add(ptr(x), c_ll(ld(x)), ptr(wpack), c_int(w_rows), ptr(bias), ptr(add),
+                                  c_ll(ld(add) if add is not None else 0), ptr(out), c_ll(ld(out)),
                                   c_int(n), c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), c_int(ks), ptr(stats),
                                   c_int(groups), c_int(1 if stats_batch else 0), ptr(ws),
                                   c_sz(ws_bytes if ws is not None else 0), ptr(_lib.err_flag(dev)), stream_ptr()))
@@ -144,9 +146,31 @@ def convT2_dgrad(dy, wpack, w_rows, cin, out=None):
     return out
 
 
+def _pad_w16(x, dy, up):
+    """The weight-gradient kernels run K along rows of W positions in steps of 16 (whole small planes when W <= 16).  Rows
+    whose width is not a multiple of 16 (the 160x192x160 volumes of BASELINE config 5: W = 40, 20 at levels 2-3) are
+    zero-padded along W: padded dY columns contribute nothing and padded X columns equal the convolution's own zero
+    padding, so the sum over voxels is unchanged.  `up`: dy is `up` times finer than x (2 for ConvTranspose)."""
+    w = x.shape[3]
+    if w % 16 == 0 or w <= 16:
+        return x, dy
+    pw = roundup(w, 16) - w
+    xp = torch.nn.functional.pad(x, (0, 0, 0, pw))
+    dyp = torch.nn.functional.pad(dy, (0, 0, 0, up * pw))
+    return xp, dyp
+
+
 def conv_wgrad(x, dy, cin_real, cout, ks, dw=None, accumulate=False):
     """fp32 weight gradient in the reference layout [Cout, Cin, k, k, k].  x may carry zero-padded channels beyond
     cin_real (its whole channel extent is contracted, only the first cin_real rows are written)."""
+    if ks == 1 and (x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]) % 16 != 0 and x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] > 16:
+        # pointwise: every voxel is just a K row; flatten and zero-pad the voxel count to a multiple of 16
+        v = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+        pv = roundup(v, 16) - v
+        x = torch.nn.functional.pad(x.reshape(1, 1, 1, v, x.shape[-1]), (0, 0, 0, pv))
+        dy = torch.nn.functional.pad(dy.reshape(1, 1, 1, v, dy.shape[-1]), (0, 0, 0, pv))
+    else:
+        x, dy = _pad_w16(x, dy, 1)
     n, d, h, w, cin = x.shape
     dev = x.device
     if dw is None:
@@ -164,6 +188,7 @@ def conv_wgrad(x, dy, cin_real, cout, ks, dw=None, accumulate=False):
 
 def convT2_wgrad(x, dy, cin, cout, dw=None, accumulate=False):
     """fp32 ConvTranspose3d(k2,s2) weight gradient [Cin, Cout, 2, 2, 2]; x coarse [N,D,H,W,Cin], dy fine [N,2D,2H,2W,Cout]."""
+    x, dy = _pad_w16(x, dy, 2)
     n, d, h, w, _ = x.shape
     dev = x.device
     if dw is None:

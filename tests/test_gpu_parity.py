@@ -317,3 +317,21 @@ def test_packed_weight_cache_is_per_parameter():
     assert _rel_l2(outs[2], outs[0]) < 3e-2 and _rel_l2(outs[3], outs[1]) < 3e-2     # same weights -> same logits
     assert _rel_l2(outs[1], outs[0]) > 0.3                                            # different weights -> different logits
     functional.clear_pack_cache()
+
+
+def test_unet_width_not_multiple_of_16_vs_oracle():
+    """W = 96 gives levels of width 48, 24, 12, 6, 3: the weight-gradient kernels' zero-padding path (ops._pad_w16) and the
+    ragged tiles of every conv kernel (BASELINE config 5 runs 160x192x160 volumes)."""
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(4, 4, feats, seed=9)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 4, 32, 64, 96, generator=g)
+    y = torch.randint(0, 4, (1, 32, 64, 96), generator=g)
+    model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), sd).train()
+    main, deep = model(x.to(DEV))
+    loss = U.DeepSupervisionLoss3D()((main, deep), y.to(DEV))
+    loss.backward()
+    rmain, rdeep, rloss, rgrads, _ = _oracle_train(sd, x, y, feats)
+    assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
+    assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss)
+    _check_grads(model, rgrads, "ragged_w", _oracle_autocast_grads(sd, x, y, feats))
