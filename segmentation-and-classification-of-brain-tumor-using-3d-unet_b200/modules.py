@@ -73,6 +73,7 @@ class _DoubleConvImpl:
     def bwd(self, saved, gouts, p):
         dout = _as_ndhwc(gouts[0].contiguous())
         dx, grads = Fn.double_conv_bwd(saved, dout, p, "", need_dx=True)
+        ops.wgrad_join()
         return [ops.to_ncdhw_f32(dx)[:, :self.cin]], grads
 
 
@@ -117,6 +118,7 @@ class _GateImpl:
     def bwd(self, saved, gouts, p):
         dout = _as_ndhwc(gouts[0].contiguous())
         dg, dx, grads = Fn.gate_bwd(saved, dout, p, "")
+        ops.wgrad_join()
         return [ops.to_ncdhw_f32(dg), ops.to_ncdhw_f32(dx)], grads
 
 
@@ -171,6 +173,7 @@ class _UNetImpl:
             k = p["final_conv.3.weight"].shape[0]
             dmain = torch.zeros((x.shape[0], k) + tuple(x.shape[1:4]), dtype=torch.float32, device=x.device)
         grads = Fn.unet_bwd(saved, dmain, list(gouts[1:]), p, list(self.model.features), on_grads=self.model._on_grads)
+        ops.wgrad_join()
         if self.model._on_backward_end is not None:
             self.model._on_backward_end()  # data parallel: join the gradient all-reduces before autograd sees the grads
         return [None], grads

@@ -48,6 +48,9 @@ class GradientBuckets:
             ev = torch.cuda.Event()
             ev.record()  # the gradients were produced on the current (compute) stream
             self.comm_stream.wait_event(ev)
+            from . import ops as _ops
+            if _ops.WGRAD_STREAM is not None:   # ... or on the weight-gradient side stream
+                self.comm_stream.wait_stream(_ops.WGRAD_STREAM)
             ctx = torch.cuda.stream(self.comm_stream)
         else:
             ctx = _Null()
