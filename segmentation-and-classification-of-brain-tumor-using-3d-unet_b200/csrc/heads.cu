@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) ds_head_fwd_kernel(const bf16* __restrict
 // backward of the 1x1 head: dl is PLANAR fp32 [N][K][Vs]; dskip[n][v][c] (+)= Σ_k dl_k W[k][c];
 // dW[k][c] += Σ dl_k skip_c ; db[k] += Σ dl_k   (fp32 atomics into caller-zeroed buffers)
 template <bool ACC>
-__global__ void __launch_bounds__(256) ds_head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) ds_head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x,
                                                           long long ldx, const float* __restrict__ w, bf16* __restrict__ dx,
                                                           long long lddx, float* __restrict__ dW, float* __restrict__ db,
                                                           int N, long long Vs, int C) {
@@ -82,11 +82,6 @@ __global__ void __launch_bounds__(256) ds_head_bwd_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) gw[k][j] = 0.f;
   float gb[KCLS] = {0.f, 0.f, 0.f, 0.f};
-  float wr[KCLS][8];  // this lane's weights (its channel chunk is fixed when nchunks == 1): no bank-conflicted LDS in the loop
-#pragma unroll
-  for (int k = 0; k < KCLS; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[k][j] = (lc < C8) ? sw[k * C + lc * 8 + j] : 0.f;
   for (long long v0 = warp_id * vpw; v0 < NV; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     if (v >= NV) continue;
@@ -106,7 +101,7 @@ __global__ void __launch_bounds__(256) ds_head_bwd_kernel(const float* __restric
       for (int j = 0; j < 8; ++j) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < KCLS; ++k) s = fmaf(g[k], (nchunks == 1) ? wr[k][j] : sw[k * C + c8 * 8 + j], s);
+        for (int k = 0; k < KCLS; ++k) s = fmaf(g[k], sw[k * C + c8 * 8 + j], s);
         o[j] = ACC ? o[j] + s : s;
       }
       stg16(dx + v * lddx + c8 * 8, pack8(o));
@@ -405,7 +400,7 @@ int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* 
   B3D_REQUIRE(K == KCLS, "ds_head: only %d output classes supported (got %d)", KCLS, K);
   B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
   const size_t smem = (2 * KCLS * C + KCLS) * sizeof(float);
-  const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 4);
+  const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 6);
   if (accumulate) { ds_head_bwd_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C); ++g_b3d_launches; }
   else { ds_head_bwd_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C); ++g_b3d_launches; }
   B3D_CHECK_CUDA(cudaGetLastError());

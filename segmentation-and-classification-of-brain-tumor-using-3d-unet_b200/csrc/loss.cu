@@ -120,6 +120,70 @@ __global__ void __launch_bounds__(256) loss_boundary_kernel(const float* __restr
   if (threadIdx.x == 0) atomicAdd(&acc[(long long)n * ACC_STRIDE + 14], (double)s_acc);
 }
 
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// pass 2, 4 voxels (consecutive x) per thread with 128-bit loads / stores (W % 4 == 0)
+__global__ void __launch_bounds__(256) loss_boundary_vec4_kernel(const float* __restrict__ prob, const long long* __restrict__ target,
+                                                                 float* __restrict__ E, double* __restrict__ acc, int D, int H, int W) {
+  __shared__ float s_acc;
+  if (threadIdx.x == 0) s_acc = 0.f;
+  __syncthreads();
+  const long long HW = (long long)H * W, V = (long long)D * HW;
+  const int n = blockIdx.y;
+  const float* pn = prob + (long long)n * KC * V;
+  float* En = E + (long long)n * KC * V;
+  const long long* tn = target + (long long)n * V;
+  float a = 0.f;
+  const long long V4 = V / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < V4; q += (long long)gridDim.x * blockDim.x) {
+    const long long v = q * 4;
+    const int x0 = (int)(v % W);
+    const int y = (int)((v / W) % H);
+    const int z = (int)(v / HW);
+    const bool hz = z + 1 < D, hy = y + 1 < H, hxp = x0 + 4 < W;
+    int t[4], tz[4], ty[4];
+    {
+      const longlong2 ta = __ldg(reinterpret_cast<const longlong2*>(tn + v)), tb = __ldg(reinterpret_cast<const longlong2*>(tn + v + 2));
+      t[0] = (int)ta.x; t[1] = (int)ta.y; t[2] = (int)tb.x; t[3] = (int)tb.y;
+      if (hz) { const longlong2 a2 = __ldg(reinterpret_cast<const longlong2*>(tn + v + HW)), b2 = __ldg(reinterpret_cast<const longlong2*>(tn + v + HW + 2));
+                tz[0] = (int)a2.x; tz[1] = (int)a2.y; tz[2] = (int)b2.x; tz[3] = (int)b2.y; }
+      if (hy) { const longlong2 a2 = __ldg(reinterpret_cast<const longlong2*>(tn + v + W)), b2 = __ldg(reinterpret_cast<const longlong2*>(tn + v + W + 2));
+                ty[0] = (int)a2.x; ty[1] = (int)a2.y; ty[2] = (int)b2.x; ty[3] = (int)b2.y; }
+    }
+    const int txp = hxp ? (int)__ldg(tn + v + 4) : -1;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      const float* pc = pn + c * V + v;
+      const float4 p4 = ld4(pc);
+      const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+      float bp[4] = {0.f, 0.f, 0.f, 0.f}, bo[4] = {0.f, 0.f, 0.f, 0.f};
+      if (hz) { const float4 q4 = ld4(pc + HW); const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { bp[i] += fabsf(qv[i] - p[i]); bo[i] += ((tz[i] == c) != (t[i] == c)) ? 1.f : 0.f; } }
+      if (hy) { const float4 q4 = ld4(pc + W); const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { bp[i] += fabsf(qv[i] - p[i]); bo[i] += ((ty[i] == c) != (t[i] == c)) ? 1.f : 0.f; } }
+      const float pxp = hxp ? __ldg(pc + 4) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < 3 || hxp) {
+          const float nb = (i < 3) ? p[i < 3 ? i + 1 : 3] : pxp;
+          const int tn1 = (i < 3) ? t[i < 3 ? i + 1 : 3] : txp;
+          bp[i] += fabsf(nb - p[i]); bo[i] += ((tn1 == c) != (t[i] == c)) ? 1.f : 0.f;
+        }
+      }
+      float e[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { e[i] = bp[i] - bo[i]; a = fmaf(e[i], e[i], a); }
+      *reinterpret_cast<float4*>(En + c * V + v) = make_float4(e[0], e[1], e[2], e[3]);
+    }
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc, a);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&acc[(long long)n * ACC_STRIDE + 14], (double)s_acc);
+}
+
 // values[0..5] = total, dice, focal, boundary, ce, tversky     (tiny, one thread)
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, int N, long long V, LossCfg cfg, float* __restrict__ values) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -230,7 +294,6 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 
 // backward, 4 voxels (consecutive x) per thread: the 7-point boundary stencil is served by 128-bit loads (W % 4 == 0)
 __device__ __forceinline__ float sgnf(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
-__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __global__ void __launch_bounds__(256) loss_bwd_vec4_kernel(const float* __restrict__ prob, const float* __restrict__ E,
                                                             const long long* __restrict__ target, const double* __restrict__ acc,
@@ -415,7 +478,14 @@ int b3d_loss_fwd(const float* logits, const long long* target, const float* cfg1
   B3D_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_STRIDE * N, st));
   dim3 grid(std::max(1, ls_blocks(V, 256) / std::max(1, N)), N);
   loss_softmax_kernel<<<grid, 256, 0, st>>>(logits, target, prob, acc, V, cfg); ++g_b3d_launches;
-  if (cfg.w_boundary != 0.f) { loss_boundary_kernel<<<grid, 256, 0, st>>>(prob, target, E, acc, D, H, W); ++g_b3d_launches; }
+  if (cfg.w_boundary != 0.f) {
+    if (W % 4 == 0 && (((uintptr_t)prob | (uintptr_t)E | (uintptr_t)target) & 15) == 0) {
+      dim3 g4(std::max(1, ls_blocks(V / 4, 256) / std::max(1, N)), N);
+      loss_boundary_vec4_kernel<<<g4, 256, 0, st>>>(prob, target, E, acc, D, H, W); ++g_b3d_launches;
+    } else {
+      loss_boundary_kernel<<<grid, 256, 0, st>>>(prob, target, E, acc, D, H, W); ++g_b3d_launches;
+    }
+  }
   loss_finalize_kernel<<<1, 32, 0, st>>>(acc, N, V, cfg, values); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
