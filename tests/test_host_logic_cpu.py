@@ -1,0 +1,56 @@
+"""Host-side logic of the package that needs no GPU: the weight-gradient zero-padding rule, the per-parameter packed-weight
+cache and its invalidation, and the C-side planners' invariants mirrored in Python."""
+import torch
+
+import b3d  # noqa: F401  (registers the package as `unet3d_b200`)
+from unet3d_b200 import functional, ops
+
+
+def test_pad_w16_is_exact_for_the_weight_gradient():
+    """ops._pad_w16: zero-padding W to a multiple of 16 does not change  dW = sum_v X[v + tap] * dY[v]  (the padded dY
+    columns are zero, the padded X columns equal the convolution's own zero padding)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3, 5, 24, 8, generator=g)        # NDHWC, W = 24
+    dy = torch.randn(1, 3, 5, 24, 4, generator=g)
+    xp, dyp = ops._pad_w16(x, dy, 1)
+    assert xp.shape[3] == 32 and dyp.shape[3] == 32 and xp.shape[:3] == x.shape[:3]
+    assert torch.equal(xp[:, :, :, :24], x) and float(xp[:, :, :, 24:].abs().max()) == 0.0
+
+    def wgrad(a, b):
+        w = torch.zeros(b.shape[-1], a.shape[-1], 3, 3, 3, requires_grad=True)
+        torch.nn.functional.conv3d(a.permute(0, 4, 1, 2, 3), w, padding=1).backward(b.permute(0, 4, 1, 2, 3))
+        return w.grad
+    assert torch.allclose(wgrad(x, dy), wgrad(xp, dyp), atol=1e-5)
+    # transposed conv: dy is twice as fine as x
+    dyt = torch.randn(1, 6, 10, 48, 4, generator=g)
+    xq, dyq = ops._pad_w16(x, dyt, 2)
+    assert xq.shape[3] == 32 and dyq.shape[3] == 64
+    # multiples of 16 and tiny planes are left alone
+    a = torch.randn(1, 2, 2, 16, 8); b = torch.randn(1, 2, 2, 16, 4)
+    assert ops._pad_w16(a, b, 1)[0] is a
+    a = torch.randn(1, 2, 2, 6, 8); b = torch.randn(1, 2, 2, 6, 4)
+    assert ops._pad_w16(a, b, 1)[0] is a
+
+
+def test_packed_weight_cache_lives_on_the_parameter(monkeypatch):
+    calls = []
+
+    def fake_pack(w, mode):
+        calls.append((id(w), mode))
+        return torch.zeros(1), 16, 16
+    monkeypatch.setattr(ops, "pack_weight", fake_pack)
+    p = torch.nn.Parameter(torch.randn(4, 4, 3, 3, 3))
+    functional.packed(p, 0); functional.packed(p, 0)
+    assert len(calls) == 1                       # cached
+    functional.packed(p, 1)
+    assert len(calls) == 2                       # per mode
+    with torch.no_grad():
+        p.add_(1.0)                              # in-place update bumps the version counter
+    functional.packed(p, 0)
+    assert len(calls) == 3
+    functional.clear_pack_cache()                # a replayed CUDA graph changes parameters behind the version counters
+    functional.packed(p, 0)
+    assert len(calls) == 4
+    q = torch.nn.Parameter(p.detach().clone())   # another parameter never sees p's cache
+    functional.packed(q, 0)
+    assert len(calls) == 5 and "_b3d_pack" in q.__dict__ and q.__dict__["_b3d_pack"] is not p.__dict__["_b3d_pack"]
