@@ -49,6 +49,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Σ over the lanes of a warp that share (lane % group), group a power of two <= 32 (32: no-op).  Every lane must call it.
+// Used before block-level fp64 shared atomics so that only `group` lanes per warp contend (and the sum stays order-fixed).
+__device__ __forceinline__ float warp_sum_mod(float v, int group) {
+  for (int o = 16; o >= group; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

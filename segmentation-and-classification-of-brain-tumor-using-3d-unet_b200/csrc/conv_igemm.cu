@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   const uint32_t tfull0 = empty0 + 8 * IG_MAXSTAGES;
   const uint32_t tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * IG_MAXSTAGES + 32);
-  float* s_stats = reinterpret_cast<float*>(aux + 16 * IG_MAXSTAGES + 48);  // [64]
+  double* s_stats = reinterpret_cast<double*>(aux + 16 * IG_MAXSTAGES + 48);  // [64], fp64: warp arrival order cannot change the sums
 
   if (threadIdx.x == 0) {
     if (sA & 1023u) { if (P.err) atomicExch(P.err, 9); __trap(); }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
     mbar_fence_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) s_stats[threadIdx.x - 64] = 0.f;
+  if (threadIdx.x >= 64 && threadIdx.x < 128) s_stats[threadIdx.x - 64] = 0.0;
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), P.tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
           const float s1 = warp_sum(a1[i]), s2 = warp_sum(a2[i]);
           if (lane == 0) {
             const int gl = (cur_n0 + i * gran) / cpg - cur_n0 / cpg;  // group slot local to this n-block
-            atomicAdd(&s_stats[2 * gl], s1);
-            atomicAdd(&s_stats[2 * gl + 1], s2);
+            atomicAdd(&s_stats[2 * gl], (double)s1);
+            atomicAdd(&s_stats[2 * gl + 1], (double)s2);
           }
         }
         a1[i] = 0.f; a2[i] = 0.f;
@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         const int g = cur_n0 / cpg + (et >> 1);
         if (g < P.stats_groups) {
           const int ns = P.stats_batch ? 0 : cur_n;
-          atomicAdd(P.stats + ((long long)ns * P.stats_groups + g) * 2 + (et & 1), (double)s_stats[et]);
+          atomicAdd(P.stats + ((long long)ns * P.stats_groups + g) * 2 + (et & 1), s_stats[et]);
         }
-        s_stats[et] = 0.f;
+        s_stats[et] = 0.0;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -380,11 +380,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
 __global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, long long V, int Cout, long long vox_per_sample,
                                       const float* __restrict__ bias, bf16* __restrict__ out, long long ld_out,
                                       double* __restrict__ stats, int cpg, int stats_groups, int stats_batch) {
-  __shared__ float s_acc[2 * 64];
+  __shared__ double s_acc[2 * 64];   // fp64: thread arrival order cannot change the sums
   const int chunks = Cout / 8;
   const long long total = V * chunks;
   // each block handles a contiguous run of voxels of ONE sample (host guarantees blockDim*iters divides evenly enough)
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
   const long long per_block = (total + gridDim.x - 1) / gridDim.x;
   const long long beg = per_block * blockIdx.x;
@@ -420,8 +420,8 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, 
           __syncthreads();
           for (int i = threadIdx.x; i < 2 * (Cout / cpg) && i < 128; i += blockDim.x) {
             const int ns = stats_batch ? 0 : cur_n;
-            atomicAdd(stats + ((long long)ns * stats_groups + (i >> 1)) * 2 + (i & 1), (double)s_acc[i]);
-            s_acc[i] = 0.f;
+            atomicAdd(stats + ((long long)ns * stats_groups + (i >> 1)) * 2 + (i & 1), s_acc[i]);
+            s_acc[i] = 0.0;
           }
           __syncthreads();
           cur_n = nn;
@@ -431,13 +431,13 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, 
             float s1 = 0.f, s2 = 0.f;
             for (int j = 0; j < 8; ++j) { s1 += v[j]; s2 += v[j] * v[j]; }
             const int g = (c8 * 8) / cpg;
-            atomicAdd(&s_acc[2 * g], s1); atomicAdd(&s_acc[2 * g + 1], s2);
+            atomicAdd(&s_acc[2 * g], (double)s1); atomicAdd(&s_acc[2 * g + 1], (double)s2);
           } else {
             for (int j0 = 0; j0 < 8; j0 += cpg) {
               float s1 = 0.f, s2 = 0.f;
               for (int j = j0; j < j0 + cpg; ++j) { s1 += v[j]; s2 += v[j] * v[j]; }
               const int g = (c8 * 8 + j0) / cpg;
-              atomicAdd(&s_acc[2 * g], s1); atomicAdd(&s_acc[2 * g + 1], s2);
+              atomicAdd(&s_acc[2 * g], (double)s1); atomicAdd(&s_acc[2 * g + 1], (double)s2);
             }
           }
         }
@@ -448,7 +448,7 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, 
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * (Cout / cpg) && i < 128; i += blockDim.x) {
       const int ns = stats_batch ? 0 : cur_n;
-      atomicAdd(stats + ((long long)ns * stats_groups + (i >> 1)) * 2 + (i & 1), (double)s_acc[i]);
+      atomicAdd(stats + ((long long)ns * stats_groups + (i >> 1)) * 2 + (i & 1), s_acc[i]);
     }
   }
 }
@@ -701,7 +701,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
     int rc = b3d_encode_tmap_bf16(&P.tmW, wpack, 4, dims, strides, box, RB);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)P.stages * P.stage_bytes + std::max<size_t>((size_t)pl.over, 16 * IG_MAXSTAGES + 48 + 64 * 4 + 128) + 1024;
+  const size_t smem = (size_t)P.stages * P.stage_bytes + std::max<size_t>((size_t)pl.over, 16 * IG_MAXSTAGES + 48 + 64 * 8 + 128) + 1024;
   B3D_REQUIRE(smem <= 227 * 1024, "igemm: smem %zu too large", smem);
   const int grid = std::min(P.num_items, num_sms);
   if (getenv("B3D_VERBOSE"))

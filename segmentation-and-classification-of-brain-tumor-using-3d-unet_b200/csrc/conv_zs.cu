@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
   const uint32_t wfree = wfull + 8;
   const uint32_t hs0 = wfree + 8;                        // [2] issue hand-shake between the two MMA warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 32);
-  float* s_stats = reinterpret_cast<float*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 48);  // [2 * 64]
+  // fp64 so that the order in which the 8 epilogue warps add their (fixed-order fp32) partial sums cannot change the result
+  double* s_stats = reinterpret_cast<double*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 48);  // [2 * 64]
 
   if (threadIdx.x == 0) {
     if (sW & 1023u) { if (P.err) atomicExch(P.err, 29); __trap(); }
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
     mbar_init(hs0, 1); mbar_init(hs0 + 8, 1);
     mbar_fence_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 192) s_stats[threadIdx.x - 64] = 0.f;
+  if (threadIdx.x >= 64 && threadIdx.x < 192) s_stats[threadIdx.x - 64] = 0.0;
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -369,8 +370,8 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
             const float s1 = warp_sum(a1[i]), s2 = warp_sum(a2[i]);
             if (lane == 0) {
               const int gl = (i * gran) / cpg;  // group local to this channel block
-              atomicAdd(&s_stats[2 * gl], s1);
-              atomicAdd(&s_stats[2 * gl + 1], s2);
+              atomicAdd(&s_stats[2 * gl], (double)s1);
+              atomicAdd(&s_stats[2 * gl + 1], (double)s2);
             }
           }
           a1[i] = 0.f; a2[i] = 0.f;
@@ -381,9 +382,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
           const int gi = c_base / cpg + (et >> 1);
           if (gi < P.stats_groups) {
             const int ns = P.stats_batch ? 0 : n;
-            atomicAdd(P.stats + ((long long)ns * P.stats_groups + gi) * 2 + (et & 1), (double)s_stats[et]);
+            atomicAdd(P.stats + ((long long)ns * P.stats_groups + gi) * 2 + (et & 1), s_stats[et]);
           }
-          s_stats[et] = 0.f;
+          s_stats[et] = 0.0;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -421,7 +422,7 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
   const int RB = KC * 2;
   const int k_chunks = Cin / KC;
   const uint32_t a_stage = (uint32_t)(ZS_BOX * RB + 1023) / 1024 * 1024;
-  const size_t aux_bytes = 16 * ZS_MAXSTAGES + 16 * 32 + 32 + 128 * 4 + 64;
+  const size_t aux_bytes = 16 * ZS_MAXSTAGES + 16 * 32 + 32 + 128 * 8 + 64;
   const size_t budget = 227 * 1024 - 1024 - aux_bytes;
   int COUT = 0, stages = 0;
   const int forced = getenv("B3D_ZS_COUT") ? atoi(getenv("B3D_ZS_COUT")) : 0;

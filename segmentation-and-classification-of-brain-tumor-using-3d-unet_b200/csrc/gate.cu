@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
     const float* __restrict__ bpsi, float* __restrict__ psi_raw, double* __restrict__ st_psi, long long V, int F, float eps) {
   extern __shared__ float sm[];
   float* scg = sm; float* scx = sm + F; float* sh = sm + 2 * F; float* wp = sm + 3 * F;
-  __shared__ float s_red[2];
+  __shared__ double s_red[2];   // fp64: warp arrival order cannot change the forward statistics
   const int n = blockIdx.y;
   const int cpg = F / 4;
   for (int c = threadIdx.x; c < F; c += blockDim.x) {
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
     const float a = gam_g[c] * rg, b = gam_x[c] * rx;
     scg[c] = a; scx[c] = b; sh[c] = bet_g[c] - mg * a + bet_x[c] - mx * b; wp[c] = wpsi[c];
   }
-  if (threadIdx.x < 2) s_red[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2) s_red[threadIdx.x] = 0.0;
   __syncthreads();
   const float bp = bpsi[0];
   const int F8 = F >> 3;
@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
     }
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if (lane == 0) { atomicAdd(&s_red[0], s1); atomicAdd(&s_red[1], s2); }
+  if (lane == 0) { atomicAdd(&s_red[0], (double)s1); atomicAdd(&s_red[1], (double)s2); }
   __syncthreads();
-  if (threadIdx.x < 2) atomicAdd(&st_psi[(long long)n * 2 + threadIdx.x], (double)s_red[threadIdx.x]);
+  if (threadIdx.x < 2) atomicAdd(&st_psi[(long long)n * 2 + threadIdx.x], s_red[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
     const float* __restrict__ bpsi_n, const float* __restrict__ ca, bf16* __restrict__ dx, long long lddx,
     float* __restrict__ dpsin, double* __restrict__ dca, double* __restrict__ st_dpsi, long long V, int C, float eps) {
   extern __shared__ float sm[];
-  float* sca = sm; float* sdca = sm + C;
-  __shared__ float s_red[2];
+  float* sca = sm; double* sdca = reinterpret_cast<double*>(sm + C);   // fp64 block accumulators: order-independent
+  __shared__ double s_red[2];
   const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) { sca[c] = ca[(long long)n * C + c]; sdca[c] = 0.f; }
-  if (threadIdx.x < 2) s_red[threadIdx.x] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { sca[c] = ca[(long long)n * C + c]; sdca[c] = 0.0; }
+  if (threadIdx.x < 2) s_red[threadIdx.x] = 0.0;
   float mu, rstd;
   mean_rstd_from(st_psi + (long long)n * 2, (double)V, eps, mu, rstd);
   const float a = gpsi[0] * rstd, b = bpsi_n[0] - mu * a;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
           ds = fmaf(dxv, cc, ds);
           o[j] = d[j] * s * cc;
           if (nchunks == 1) acc_ca[j] = fmaf(dxv, s, acc_ca[j]);
-          else atomicAdd(&sdca[c8 * 8 + j], dxv * s);
+          else atomicAdd(&sdca[c8 * 8 + j], (double)(dxv * s));
         }
         stg16(dxn + v * lddx + c8 * 8, pack8(o));
       }
@@ -208,15 +208,19 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
       r1 += dpn; r2 += dpn * xh;
     }
   }
-  if (nchunks == 1 && lc < C8) {
+  if (nchunks == 1) {   // lanes with the same lc own the same chunk: fold them first (lanes_c is a power of two)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sdca[lc * 8 + j], acc_ca[j]);
+    for (int j = 0; j < 8; ++j) acc_ca[j] = warp_sum_mod(acc_ca[j], lanes_c);
+    if (lane < lanes_c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sdca[lc * 8 + j], (double)acc_ca[j]);
+    }
   }
   r1 = warp_sum(r1); r2 = warp_sum(r2);
-  if (lane == 0) { atomicAdd(&s_red[0], r1); atomicAdd(&s_red[1], r2); }
+  if (lane == 0) { atomicAdd(&s_red[0], (double)r1); atomicAdd(&s_red[1], (double)r2); }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dca[(long long)n * C + c], (double)sdca[c]);
-  if (threadIdx.x < 2) atomicAdd(&st_dpsi[(long long)n * 2 + threadIdx.x], (double)s_red[threadIdx.x]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dca[(long long)n * C + c], sdca[c]);
+  if (threadIdx.x < 2) atomicAdd(&st_dpsi[(long long)n * 2 + threadIdx.x], s_red[threadIdx.x]);
 }
 
 // SE backward (one block per sample).  Param grads are accumulated with fp32 atomics into caller-zeroed buffers.
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
   extern __shared__ float sm[];
   float* mg = sm; float* rg = sm + F; float* mx = sm + 2 * F; float* rx = sm + 3 * F;
   float* gg = sm + 4 * F; float* gx = sm + 5 * F; float* sh = sm + 6 * F; float* wp = sm + 7 * F;
-  float* red = sm + 8 * F;  // [4][F]: Σdz, Σdz*x̂g, Σdz*x̂x, Σdψr*q
-  __shared__ float s_db;
+  double* red = reinterpret_cast<double*>(sm + 8 * F);  // [4][F]: Σdz, Σdz*x̂g, Σdz*x̂x, Σdψr*q
+  __shared__ double s_db;
   const int n = blockIdx.y;
   const int cpg = F / 4;
   for (int c = threadIdx.x; c < F; c += blockDim.x) {
@@ -283,9 +287,9 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
     mean_rstd_from(st_x + ((long long)n * 4 + c / cpg) * 2, (double)cpg * V, eps, m2, r2);
     mg[c] = m1; rg[c] = r1; mx[c] = m2; rx[c] = r2; gg[c] = gam_g[c]; gx[c] = gam_x[c];
     sh[c] = bet_g[c] + bet_x[c]; wp[c] = wpsi[c];
-    red[c] = 0.f; red[F + c] = 0.f; red[2 * F + c] = 0.f; red[3 * F + c] = 0.f;
+    red[c] = 0.0; red[F + c] = 0.0; red[2 * F + c] = 0.0; red[3 * F + c] = 0.0;
   }
-  if (threadIdx.x == 0) s_db = 0.f;
+  if (threadIdx.x == 0) s_db = 0.0;
   float mu, rstd;
   mean_rstd_from(st_psi + (long long)n * 2, (double)V, eps, mu, rstd);
   const float gp = gpsi[0];
@@ -329,31 +333,38 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
         if (nchunks == 1) {
           a0[j] += dzv; a1[j] = fmaf(dzv, xg, a1[j]); a2[j] = fmaf(dzv, xx, a2[j]); a3[j] = fmaf(dpr, qq, a3[j]);
         } else {
-          atomicAdd(&red[c], dzv); atomicAdd(&red[F + c], dzv * xg); atomicAdd(&red[2 * F + c], dzv * xx);
-          atomicAdd(&red[3 * F + c], dpr * qq);
+          atomicAdd(&red[c], (double)dzv); atomicAdd(&red[F + c], (double)(dzv * xg)); atomicAdd(&red[2 * F + c], (double)(dzv * xx));
+          atomicAdd(&red[3 * F + c], (double)(dpr * qq));
         }
       }
       stg16(dzn + v * F + c8 * 8, pack8(o));
     }
   }
-  if (nchunks == 1 && lc < F8) {
+  if (nchunks == 1) {   // fold the lanes that own the same chunk (lanes_c is a power of two), then one atomic per warp
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red[lc * 8 + j], a0[j]); atomicAdd(&red[F + lc * 8 + j], a1[j]);
-      atomicAdd(&red[2 * F + lc * 8 + j], a2[j]); atomicAdd(&red[3 * F + lc * 8 + j], a3[j]);
+      a0[j] = warp_sum_mod(a0[j], lanes_c); a1[j] = warp_sum_mod(a1[j], lanes_c);
+      a2[j] = warp_sum_mod(a2[j], lanes_c); a3[j] = warp_sum_mod(a3[j], lanes_c);
+    }
+    if (lane < lanes_c) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[lc * 8 + j], (double)a0[j]); atomicAdd(&red[F + lc * 8 + j], (double)a1[j]);
+        atomicAdd(&red[2 * F + lc * 8 + j], (double)a2[j]); atomicAdd(&red[3 * F + lc * 8 + j], (double)a3[j]);
+      }
     }
   }
   db = warp_sum(db);
-  if (lane == 0) atomicAdd(&s_db, db);
+  if (lane == 0) atomicAdd(&s_db, (double)db);
   __syncthreads();
   for (int c = threadIdx.x; c < F; c += blockDim.x) {
-    atomicAdd(&sums_g[((long long)n * F + c) * 2], (double)red[c]);
-    atomicAdd(&sums_g[((long long)n * F + c) * 2 + 1], (double)red[F + c]);
-    atomicAdd(&sums_x[((long long)n * F + c) * 2], (double)red[c]);
-    atomicAdd(&sums_x[((long long)n * F + c) * 2 + 1], (double)red[2 * F + c]);
-    atomicAdd(&dwpsi[c], red[3 * F + c]);
+    atomicAdd(&sums_g[((long long)n * F + c) * 2], red[c]);
+    atomicAdd(&sums_g[((long long)n * F + c) * 2 + 1], red[F + c]);
+    atomicAdd(&sums_x[((long long)n * F + c) * 2], red[c]);
+    atomicAdd(&sums_x[((long long)n * F + c) * 2 + 1], red[2 * F + c]);
+    atomicAdd(&dwpsi[c], (float)red[3 * F + c]);
   }
-  if (threadIdx.x == 0) atomicAdd(dbpsi, s_db);
+  if (threadIdx.x == 0) atomicAdd(dbpsi, (float)s_db);
 }
 
 // dγψ = Σ_n Σ_v dψn*x̂ψ ; dβψ = Σ_n Σ_v dψn
@@ -426,7 +437,7 @@ int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long lon
                        void* stream) {
   B3D_REQUIRE(C % 8 == 0 && (pow2(C / 8) || (C / 8) % 32 == 0) && C <= 4096, "gate_apply_bwd: C=%d unsupported", C);
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
-  gate_apply_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+  gate_apply_bwd_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dout, lddo, (const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n, ca, (bf16*)dx, lddx, dpsin, dca, st_dpsi, V, C, eps); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
@@ -448,7 +459,7 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
                      int N, long long V, int F, float eps, void* stream) {
   B3D_REQUIRE(F % 8 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_bwd: F=%d unsupported", F);
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
-  gate_psi_bwd_kernel<<<grid, 256, 12 * F * sizeof(float), (cudaStream_t)stream>>>(
+  gate_psi_bwd_kernel<<<grid, 256, 16 * F * sizeof(float), (cudaStream_t)stream>>>(
       dpsin, psi_raw, st_psi, st_dpsi, gpsi, (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi,
       (bf16*)dz, sums_g, sums_x, dwpsi, dbpsi, V, F, eps); ++g_b3d_launches;
   gate_psi_norm_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st_dpsi, N, dgpsi, dbpsi_n); ++g_b3d_launches;

@@ -269,13 +269,13 @@ __global__ void __launch_bounds__(256) final_head_bwd_reduce_kernel(const float*
                                                                     long long V) {
   constexpr int NR = 2 * F2 + KCLS * F2 + KCLS;
   __shared__ float s_mean[F2], s_rstd[F2], s_g[F2], s_bt[F2], s_w[KCLS * F2];
-  __shared__ float s_red[NR];
+  __shared__ double s_red[NR];   // fp64: warp arrival order cannot change the BatchNorm-backward sums
   if (threadIdx.x < F2) {
     s_mean[threadIdx.x] = bn[threadIdx.x]; s_rstd[threadIdx.x] = bn[F2 + threadIdx.x];
     s_g[threadIdx.x] = gamma[threadIdx.x]; s_bt[threadIdx.x] = beta[threadIdx.x];
   }
   for (int i = threadIdx.x; i < KCLS * F2; i += blockDim.x) s_w[i] = w2[i];
-  for (int i = threadIdx.x; i < NR; i += blockDim.x) s_red[i] = 0.f;
+  for (int i = threadIdx.x; i < NR; i += blockDim.x) s_red[i] = 0.0;
   __syncthreads();
   float a_dz[F2], a_dzx[F2], a_w[KCLS][F2], a_b[KCLS];
 #pragma unroll
@@ -314,20 +314,20 @@ __global__ void __launch_bounds__(256) final_head_bwd_reduce_kernel(const float*
 #pragma unroll
   for (int c = 0; c < F2; ++c) {
     const float s1 = warp_sum(a_dz[c]), s2 = warp_sum(a_dzx[c]);
-    if (lane == 0) { atomicAdd(&s_red[c], s1); atomicAdd(&s_red[F2 + c], s2); }
+    if (lane == 0) { atomicAdd(&s_red[c], (double)s1); atomicAdd(&s_red[F2 + c], (double)s2); }
   }
 #pragma unroll
   for (int k = 0; k < KCLS; ++k) {
 #pragma unroll
     for (int c = 0; c < F2; ++c) {
       const float s = warp_sum(a_w[k][c]);
-      if (lane == 0) atomicAdd(&s_red[2 * F2 + k * F2 + c], s);
+      if (lane == 0) atomicAdd(&s_red[2 * F2 + k * F2 + c], (double)s);
     }
     const float sb = warp_sum(a_b[k]);
-    if (lane == 0) atomicAdd(&s_red[2 * F2 + KCLS * F2 + k], sb);
+    if (lane == 0) atomicAdd(&s_red[2 * F2 + KCLS * F2 + k], (double)sb);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NR; i += blockDim.x) atomicAdd(&red[i], (double)s_red[i]);
+  for (int i = threadIdx.x; i < NR; i += blockDim.x) atomicAdd(&red[i], s_red[i]);
 }
 
 // backward phase 2: dh = BN-backward(dz) as bf16 [N][V][F2]; train uses batch statistics, eval the running ones

@@ -37,8 +37,8 @@ __device__ __forceinline__ float focal_pow(float base, float gamma) {
 __global__ void __launch_bounds__(256) loss_softmax_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                                            float* __restrict__ prob, double* __restrict__ acc, long long V,
                                                            LossCfg cfg) {
-  __shared__ float s_acc[14];
-  if (threadIdx.x < 14) s_acc[threadIdx.x] = 0.f;
+  __shared__ double s_acc[14];   // fp64: warp arrival order cannot change the loss sums
+  if (threadIdx.x < 14) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
   const int n = blockIdx.y;
   const float* ln = logits + (long long)n * KC * V;
@@ -74,19 +74,19 @@ __global__ void __launch_bounds__(256) loss_softmax_kernel(const float* __restri
 #pragma unroll
   for (int c = 0; c < KC; ++c) {
     const float a = warp_sum(aI[c]), b = warp_sum(aP[c]), d = warp_sum(aT[c]);
-    if (lane == 0) { atomicAdd(&s_acc[c], a); atomicAdd(&s_acc[4 + c], b); atomicAdd(&s_acc[8 + c], d); }
+    if (lane == 0) { atomicAdd(&s_acc[c], (double)a); atomicAdd(&s_acc[4 + c], (double)b); atomicAdd(&s_acc[8 + c], (double)d); }
   }
   ace = warp_sum(ace); afo = warp_sum(afo);
-  if (lane == 0) { atomicAdd(&s_acc[12], ace); atomicAdd(&s_acc[13], afo); }
+  if (lane == 0) { atomicAdd(&s_acc[12], (double)ace); atomicAdd(&s_acc[13], (double)afo); }
   __syncthreads();
-  if (threadIdx.x < 14) atomicAdd(&acc[(long long)n * ACC_STRIDE + threadIdx.x], (double)s_acc[threadIdx.x]);
+  if (threadIdx.x < 14) atomicAdd(&acc[(long long)n * ACC_STRIDE + threadIdx.x], s_acc[threadIdx.x]);
 }
 
 // pass 2: E = B(p) − B(onehot) (forward differences, zero at the far face), stored planar; acc[n][14] += ΣE²
 __global__ void __launch_bounds__(256) loss_boundary_kernel(const float* __restrict__ prob, const long long* __restrict__ target,
                                                             float* __restrict__ E, double* __restrict__ acc, int D, int H, int W) {
-  __shared__ float s_acc;
-  if (threadIdx.x == 0) s_acc = 0.f;
+  __shared__ double s_acc;
+  if (threadIdx.x == 0) s_acc = 0.0;
   __syncthreads();
   const long long V = (long long)D * H * W;
   const int n = blockIdx.y;
@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(256) loss_boundary_kernel(const float* __restr
     }
   }
   a = warp_sum(a);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc, a);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc, (double)a);
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(&acc[(long long)n * ACC_STRIDE + 14], (double)s_acc);
+  if (threadIdx.x == 0) atomicAdd(&acc[(long long)n * ACC_STRIDE + 14], s_acc);
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -125,8 +125,8 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 // pass 2, 4 voxels (consecutive x) per thread with 128-bit loads / stores (W % 4 == 0)
 __global__ void __launch_bounds__(256) loss_boundary_vec4_kernel(const float* __restrict__ prob, const long long* __restrict__ target,
                                                                  float* __restrict__ E, double* __restrict__ acc, int D, int H, int W) {
-  __shared__ float s_acc;
-  if (threadIdx.x == 0) s_acc = 0.f;
+  __shared__ double s_acc;
+  if (threadIdx.x == 0) s_acc = 0.0;
   __syncthreads();
   const long long HW = (long long)H * W, V = (long long)D * HW;
   const int n = blockIdx.y;
@@ -179,9 +179,9 @@ __global__ void __launch_bounds__(256) loss_boundary_vec4_kernel(const float* __
     }
   }
   a = warp_sum(a);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc, a);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc, (double)a);
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(&acc[(long long)n * ACC_STRIDE + 14], (double)s_acc);
+  if (threadIdx.x == 0) atomicAdd(&acc[(long long)n * ACC_STRIDE + 14], s_acc);
 }
 
 // values[0..5] = total, dice, focal, boundary, ce, tversky     (tiny, one thread)

@@ -124,13 +124,13 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
     double* __restrict__ sums, long long V, int C, float eps) {
   extern __shared__ float sm[];
   float* s_mean = sm; float* s_rstd = sm + C; float* s_g = sm + 2 * C; float* s_b = sm + 3 * C;
-  float* red = sm + 4 * C;  // [2][C] block accumulators
+  double* red = reinterpret_cast<double*>(sm + 4 * C);  // [2][C] block accumulators (fp64: arrival order cannot change dX)
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     gn_mean_rstd(stats, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
     s_mean[c] = mean; s_rstd[c] = rstd; s_g[c] = gamma[c]; s_b[c] = beta[c];
-    red[c] = 0.f; red[C + c] = 0.f;
+    red[c] = 0.0; red[C + c] = 0.0;
   }
   __syncthreads();
   const int C8 = C >> 3;
@@ -190,18 +190,25 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(
         const float xh = (x[j] - s_mean[c0 + j]) * s_rstd[c0 + j];
         float dz = d[j];
         if (RELU && fmaf(xh, s_g[c0 + j], s_b[c0 + j]) <= 0.f) dz = 0.f;
-        atomicAdd(&red[c0 + j], dz); atomicAdd(&red[C + c0 + j], dz * xh);
+        atomicAdd(&red[c0 + j], (double)dz); atomicAdd(&red[C + c0 + j], (double)(dz * xh));
       }
     }
   }
-  if (fixed && myc0 >= 0) {
+  if (fixed) {   // lanes l, l + C8, ... of a warp own the same chunk: fold them with shuffles, one fp64 atomic per warp and channel
+    const int grp = C8 < 32 ? C8 : 32;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(&red[myc0 + j], a1[j]); atomicAdd(&red[C + myc0 + j], a2[j]); }
+    for (int j = 0; j < 8; ++j) { a1[j] = warp_sum_mod(a1[j], grp); a2[j] = warp_sum_mod(a2[j], grp); }
+    if (lane < grp) {
+      const int c0 = (int)(threadIdx.x % C8) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&red[c0 + j], (double)a1[j]); atomicAdd(&red[C + c0 + j], (double)a2[j]); }
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&sums[((long long)n * C + c) * 2], (double)red[c]);
-    atomicAdd(&sums[((long long)n * C + c) * 2 + 1], (double)red[C + c]);
+    atomicAdd(&sums[((long long)n * C + c) * 2], red[c]);
+    atomicAdd(&sums[((long long)n * C + c) * 2 + 1], red[C + c]);
   }
 }
 
@@ -351,7 +358,7 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
   B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0, "gn_bwd_reduce: bad C=%d G=%d", C, G);
   const int per_sample = std::max(1, std::min(ew_blocks(V * (C / 8), GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
   dim3 grid(per_sample, N);
-  const size_t smem = 6 * (size_t)C * sizeof(float);
+  const size_t smem = 8 * (size_t)C * sizeof(float);   // 4C floats + 2C doubles
   cudaStream_t st = (cudaStream_t)stream;
   if (relu) { gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }
   else { gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }

@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(256) to_ncdhw_kernel(const bf16* __restrict__ 
 // sums[n][c] += Σ_v x[n][v][c]     (double atomics; caller zeroes)  — SE average pool and bias gradients
 __global__ void __launch_bounds__(256) channel_sum_kernel(const bf16* __restrict__ x, long long ldx, double* __restrict__ sums,
                                                           long long V, int C) {
-  extern __shared__ float red[];  // [C]
+  extern __shared__ double red[];  // [C], fp64: thread arrival order cannot change the sums (forward SE mean)
   const int n = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) red[c] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) red[c] = 0.0;
   __syncthreads();
   const int C8 = C >> 3;
   const bool fixed = (blockDim.x % C8) == 0;
@@ -182,15 +182,21 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const bf16* __restrict
       for (int j = 0; j < 8; ++j) acc[j] += a[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], a[j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], (double)a[j]);
     }
   }
-  if (fixed && myc0 >= 0) {
+  if (fixed) {   // fold the lanes of a warp that own the same chunk, then one fp64 atomic per warp and channel
+    const int grp = C8 < 32 ? C8 : 32;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red[myc0 + j], acc[j]);
+    for (int j = 0; j < 8; ++j) acc[j] = warp_sum_mod(acc[j], grp);
+    if ((int)(threadIdx.x & 31) < grp) {
+      const int c0 = (int)(threadIdx.x % C8) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[c0 + j], (double)acc[j]);
+    }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&sums[(long long)n * C + c], (double)red[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&sums[(long long)n * C + c], red[c]);
 }
 
 extern "C" {
@@ -233,7 +239,7 @@ int b3d_channel_sum(const void* x, long long ldx, double* sums, int N, long long
   B3D_REQUIRE(C % 8 == 0 && C <= 4096, "channel_sum: bad C");
   const int per_sample = std::max(1, std::min(ew_blocks2(V * (C / 8), 256 * 8), b3d_num_sms() * 4 / std::max(1, N)));
   dim3 grid(per_sample, N);
-  channel_sum_kernel<<<grid, 256, C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, ldx, sums, V, C); ++g_b3d_launches;
+  channel_sum_kernel<<<grid, 256, C * sizeof(double), (cudaStream_t)stream>>>((const bf16*)x, ldx, sums, V, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

@@ -56,9 +56,12 @@ class GradientBuckets:
             ctx = _Null()
         with ctx:
             flat = torch.cat([t.reshape(-1).float() for t in tensors])
-            if self.average:
-                flat.div_(self.world())
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if self.average and cuda:   # NCCL averages inside the collective: no separate pass over the bucket
+                work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            else:
+                if self.average:
+                    flat.div_(self.world())
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.inflight.append((work, flat, tensors))
             if cuda:
                 for t in tensors:

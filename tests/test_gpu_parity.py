@@ -335,3 +335,40 @@ def test_unet_width_not_multiple_of_16_vs_oracle():
     assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
     assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss)
     _check_grads(model, rgrads, "ragged_w", _oracle_autocast_grads(sd, x, y, feats))
+
+
+def test_run_to_run_reproducibility():
+    """Two identical train passes: the forward (logits, deep-supervision maps, loss) is bit-identical and every parameter
+    gradient agrees to fp32 rounding.  The block-level reductions that feed activations or input gradients (conv-epilogue
+    GroupNorm/BatchNorm sums, GroupNorm-backward sums, gate and loss sums) accumulate fixed-order fp32 partials in fp64, so
+    the arrival order of warps/CTAs cannot flip a bf16 rounding downstream; only the weight-gradient flush (leaves of the
+    backward graph) still uses fp32 atomics.  Before this, a single 1-ulp flip at a 4^3 level grew to 15 % run-to-run
+    differences in deep-level weight gradients (scripts/diverge_check.py, scripts/jitter_check.py)."""
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(4, 4, feats, seed=11)
+    x, y = O.make_inputs(2, 32, 32, 32, seed=11)
+    xd, yd = x.to(DEV), y.to(DEV)
+    model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), sd).train()
+    crit = U.DeepSupervisionLoss3D()
+    runs = []
+    for _ in range(3):
+        model.zero_grad(set_to_none=True)
+        main, deep = model(xd)
+        loss = crit((main, deep), yd)
+        loss.backward()
+        torch.cuda.synchronize()
+        runs.append((main.detach().clone(), [d.detach().clone() for d in deep], loss.detach().clone(),
+                     {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}))
+    a = runs[0]
+    total = float(torch.sqrt(sum((g.double() ** 2).sum() for g in a[3].values())))
+    for b in runs[1:]:
+        assert torch.equal(a[0], b[0]), "main logits differ between two identical runs"
+        assert all(torch.equal(p, q) for p, q in zip(a[1], b[1])), "deep-supervision outputs differ between identical runs"
+        assert torch.equal(a[2], b[2]), "loss differs between identical runs"
+        for k in a[3]:
+            d = float((a[3][k] - b[3][k]).norm()) / max(float(a[3][k].norm()), 1e-3 * total)
+            assert d <= 2e-5, "gradient of %s differs by %.3g between identical runs" % (k, d)
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(xd), model(xd)
+    assert torch.equal(e1, e2), "inference logits differ between two identical runs"
