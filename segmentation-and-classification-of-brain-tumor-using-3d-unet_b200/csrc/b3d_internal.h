@@ -12,3 +12,6 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
 // conv_wg2.cu: 3x3x3 weight gradient with swizzled MN-major operands (W a multiple of 16).  Same return convention.
 int b3d_try_wg2(const void* x, long long ldx, int Cin, const void* dy, long long lddy, int Cout_pad, int N, int D, int H, int W,
                 float* dwacc, int Cin_pad, int* err_flag, cudaStream_t stream);
+// conv_wgp.cu: streaming weight gradient of 1x1x1 convs (taps = 1) and ConvTranspose3d k2 s2 (taps = 8).  Same return convention.
+int b3d_try_wgp(const void* x, long long ldx, int Cin, const void* dy, long long lddy, int Cout_pad, long long V, int taps,
+                int ND, int Hc, int Wc, float* dwacc, int Cin_pad, int* err_flag, cudaStream_t stream);

@@ -550,6 +550,8 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   int rc = 1;
   if (ks == 3 && Cin % 16 == 0)  // swizzled MN-major kernel (conv_wg2.cu) when the rows are a multiple of 16 wide
     rc = b3d_try_wg2(x, ldx, Cin, dy, lddy, Cout_pad, N, D, H, W, ws, Cin, err_flag, st);
+  else if (ks == 1)              // streaming kernel (conv_wgp.cu)
+    rc = b3d_try_wgp(x, ldx, Cin, dy, lddy, Cout_pad, (long long)N * D * H * W, 1, 0, 0, 0, ws, Cin, err_flag, st);
   if (rc < 0) return rc;
   if (rc > 0) rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
@@ -574,7 +576,9 @@ int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long ldd
     yv[t8].sW = 2 * pW; yv[t8].sH = 2 * pH; yv[t8].sND = 2 * pD;
   }
   // the N*D planes of the coarse grid: plane (n,z) of view t8 starts at n*(2D)*pD + 2z*pD = (n*D+z)*2*pD  -> uniform stride
-  int rc = run_wgrad(x, ldx, Cin, yv, 8, N, D, H, W, Cout, 1, ws, Cin, Cout_pad, err_flag, st);
+  int rc = b3d_try_wgp(x, ldx, Cin, dy, lddy, Cout_pad, (long long)N * D * H * W, 8, N * D, H, W, ws, Cin, err_flag, st);
+  if (rc < 0) return rc;
+  if (rc > 0) rc = run_wgrad(x, ldx, Cin, yv, 8, N, D, H, W, Cout, 1, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
   wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, Cin), 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());

@@ -13,7 +13,7 @@ host synchronisation, which is what makes it capturable.  The optimizer must be 
 """
 import torch
 
-from . import functional
+from . import functional, ops
 
 
 class GraphedTrainStep:
@@ -31,8 +31,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.optimizer.zero_grad(set_to_none=True)
         # thread_local: CUDA calls of other host threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
+        ops.reset_scratch()   # the capture must zero-fill its own scratch arenas (and nothing eager may slice them later)
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._eager()
+        ops.reset_scratch()
         torch.cuda.synchronize()
 
     def _eager(self):
@@ -104,8 +106,10 @@ class GraphedInference:
                 self.model(self.x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        ops.reset_scratch()
         with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out = self.model(self.x)
+        ops.reset_scratch()
         torch.cuda.synchronize()
 
     def __call__(self, x):

@@ -61,6 +61,39 @@ def new_act(n, d, h, w, c, device, zero=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# zeroed scratch: the ~130 small statistics / reduction buffers of a step (fp64 sums the kernels accumulate into with
+# atomics) are carved out of a few zero-filled arenas by a bump allocator instead of one fill kernel each.  A slice is handed
+# out once and never reused, so it is zero when its kernel runs; an arena is freed when its last slice dies.  Arenas are
+# per stream (the fill is ordered on the stream that was current when the arena was created).
+# ---------------------------------------------------------------------------------------------------------------
+_ARENA_BYTES = 1 << 18
+_arenas = {}
+
+
+def zeros_scratch(shape, dtype, device):
+    n = 1
+    for s_ in shape:
+        n *= int(s_)
+    nbytes = roundup(max(n, 1) * torch.empty((), dtype=dtype).element_size(), 256)
+    if device.type != "cuda" or nbytes > _ARENA_BYTES // 4:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    # an arena filled during a graph capture belongs to that graph (and one filled eagerly is not re-zeroed by a replay)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, torch.cuda.is_current_stream_capturing())
+    a = _arenas.get(key)
+    if a is None or a[1] + nbytes > _ARENA_BYTES:
+        a = [torch.zeros(_ARENA_BYTES, dtype=torch.uint8, device=device), 0]
+        _arenas[key] = a
+    off = a[1]
+    a[1] = off + nbytes
+    return a[0][off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+
+
+def reset_scratch():
+    """Forget the current arenas (a CUDA-graph capture must not slice an arena that was filled outside the capture)."""
+    _arenas.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # weights
 # ---------------------------------------------------------------------------------------------------------------
 PACK_FPROP, PACK_DGRAD, PACK_CONVT_FPROP, PACK_CONVT_DGRAD = 0, 1, 2, 3
@@ -107,7 +140,7 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
         out = new_act(n, d, h, w, cout, dev)
     stats = None
     if groups:
-        stats = torch.zeros((1 if stats_batch else n, groups, 2), dtype=torch.float64, device=dev)
+        stats = zeros_scratch((1 if stats_batch else n, groups, 2), torch.float64, dev)
     # split-K workspace: up to 16 fp32 partial slices [split][V][Cout]; only small (deep-level) problems ever split
     one = n * d * h * w * cout * 4
     ws_bytes = one * 16 if (one * 16 <= (1 << 26) and add is None) else 0
@@ -279,7 +312,7 @@ def gn_bwd(dy, y, stats, gamma, beta, groups, relu, dx=None, accumulate=False, s
     n, v, c = _nvc(y)
     dev = y.device
     if sums is None:
-        sums = torch.zeros((n, c, 2), dtype=torch.float64, device=dev)
+        sums = zeros_scratch((n, c, 2), torch.float64, dev)
         check(_L().b3d_gn_bwd_reduce(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta),
                                      c_int(groups), c_int(1 if relu else 0), ptr(sums), c_int(n), c_ll(v), c_int(c),
                                      c_float(EPS), stream_ptr()))
@@ -348,7 +381,7 @@ def to_ncdhw_f32(x):
 def channel_sum(x):
     """float64 [N][C] = Σ over voxels."""
     n, v, c = _nvc(x)
-    sums = torch.zeros((n, c), dtype=torch.float64, device=x.device)
+    sums = zeros_scratch((n, c), torch.float64, x.device)
     check(_L().b3d_channel_sum(ptr(x), c_ll(ld(x)), ptr(sums), c_int(n), c_ll(v), c_int(c), stream_ptr()))
     return sums
 
@@ -360,7 +393,7 @@ def gate_psi_fwd(g1r, x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi, bpsi):
     n, v, f = _nvc(g1r)
     dev = g1r.device
     psi_raw = torch.empty((n, v), dtype=torch.float32, device=dev)
-    st_psi = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+    st_psi = zeros_scratch((n, 2), torch.float64, dev)
     check(_L().b3d_gate_psi_fwd(ptr(g1r), ptr(x1r), ptr(st_g), ptr(st_x), ptr(gam_g), ptr(bet_g), ptr(gam_x), ptr(bet_x),
                                 ptr(wpsi), ptr(bpsi), ptr(psi_raw), ptr(st_psi), c_int(n), c_ll(v), c_int(f), c_float(EPS),
                                 stream_ptr()))
@@ -389,8 +422,8 @@ def gate_apply_bwd(dout, x, psi_raw, st_psi, gpsi, bpsi_n, ca, dx):
     n, v, c = _nvc(x)
     dev = x.device
     dpsin = torch.empty((n, v), dtype=torch.float32, device=dev)
-    dca = torch.zeros((n, c), dtype=torch.float64, device=dev)
-    st_dpsi = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+    dca = zeros_scratch((n, c), torch.float64, dev)
+    st_dpsi = zeros_scratch((n, 2), torch.float64, dev)
     check(_L().b3d_gate_apply_bwd(ptr(dout), c_ll(ld(dout)), ptr(x), c_ll(ld(x)), ptr(psi_raw), ptr(st_psi), ptr(gpsi),
                                   ptr(bpsi_n), ptr(ca), ptr(dx), c_ll(ld(dx)), ptr(dpsin), ptr(dca), ptr(st_dpsi), c_int(n),
                                   c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
@@ -414,8 +447,8 @@ def gate_psi_bwd(dpsin, psi_raw, st_psi, st_dpsi, gpsi, g1r, x1r, st_g, st_x, ga
     n, v, f = _nvc(g1r)
     dev = g1r.device
     dz = torch.empty_like(g1r)
-    sums_g = torch.zeros((n, f, 2), dtype=torch.float64, device=dev)
-    sums_x = torch.zeros((n, f, 2), dtype=torch.float64, device=dev)
+    sums_g = zeros_scratch((n, f, 2), torch.float64, dev)
+    sums_x = zeros_scratch((n, f, 2), torch.float64, dev)
     small = torch.zeros(f + 3, dtype=torch.float32, device=dev)  # dwpsi[f], dbpsi, dgpsi, dbpsi_n
     check(_L().b3d_gate_psi_bwd(ptr(dpsin), ptr(psi_raw), ptr(st_psi), ptr(st_dpsi), ptr(gpsi), ptr(g1r), ptr(x1r), ptr(st_g),
                                 ptr(st_x), ptr(gam_g), ptr(bet_g), ptr(gam_x), ptr(bet_x), ptr(wpsi), ptr(dz), ptr(sums_g),
@@ -497,7 +530,7 @@ def final_head_bwd(dl, h, bn, gamma, beta, w2, train):
     n, d, hh, w, f2 = h.shape
     k = w2.shape[0]
     dev = h.device
-    red = torch.zeros(2 * f2 + k * f2 + k, dtype=torch.float64, device=dev)
+    red = zeros_scratch((2 * f2 + k * f2 + k,), torch.float64, dev)
     dh = torch.empty_like(h, memory_format=torch.contiguous_format)
     dgamma = torch.empty(f2, dtype=torch.float32, device=dev)
     dbeta = torch.empty(f2, dtype=torch.float32, device=dev)

@@ -276,6 +276,11 @@ def test_confusion_and_voxel_counts_bit_exact():
     (1, 2, 2, 2, 256, 128, 1),     # pointwise with 8 voxels
     (1, 1, 1, 1, 512, 1024, 1),    # pointwise with a single voxel
     (1, 8, 32, 32, 512, 256, 1),   # wide pointwise: N block must shrink to fit shared memory
+    (2, 5, 7, 24, 64, 32, 1),      # streaming pointwise kernel (conv_wgp.cu): ragged voxel count (TMA zero fill on the last tile)
+    (1, 3, 16, 16, 16, 32, 1),     # conv_wgp: 16-channel blocks on X (32-byte swizzle)
+    (2, 16, 16, 16, 64, 48, 1),    # conv_wgp: Cout 48 = three 16-channel blocks on M
+    (1, 8, 8, 8, 1024, 512, 1),    # conv_wgp: 4 x 4 keys, several keys per CTA
+    (2, 32, 32, 64, 64, 32, 1),    # conv_wgp: many K tiles per CTA (ring wrap)
 ])
 def test_conv_wgrad(n, d, h, w, cin, cout, ks):
     x = _bf(n, d, h, w, cin, seed=31)
@@ -302,7 +307,8 @@ def test_conv_wgrad_padded_input_channels():
     assert (dw - wt.grad).abs().max().item() <= 2e-3 * wt.grad.abs().max().item() + 1e-3
 
 
-@pytest.mark.parametrize("n,s,cin,cout", [(2, 4, 64, 32), (1, 8, 32, 16), (2, 16, 64, 32), (1, 1, 512, 256), (2, 2, 256, 128)])
+@pytest.mark.parametrize("n,s,cin,cout", [(2, 4, 64, 32), (1, 8, 32, 16), (2, 16, 64, 32), (1, 1, 512, 256), (2, 2, 256, 128),
+                                          (1, 32, 64, 32), (2, 8, 512, 256), (1, 4, 1024, 512)])
 def test_convT2_wgrad(n, s, cin, cout):
     x = _bf(n, s, s, s, cin, seed=35)
     dy = _bf(n, 2 * s, 2 * s, 2 * s, cout, seed=36)
