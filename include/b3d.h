@@ -29,6 +29,11 @@ long long b3d_launch_count(void);                    /* kernels launched by this
 /* weight repack fp32 reference layout -> bf16 [K/8][taps][rows][8].
  * mode 0: nn.Conv3d fprop, 1: Conv3d dgrad (flipped+transposed), 2: ConvTranspose3d fprop, 3: ConvTranspose3d dgrad */
 int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void* out, int Kp, int rows, void* stream);
+/* both packed copies of one weight from a single read (what a training step does after every optimizer update):
+ * convT = 0: modes 0 + 1 of an nn.Conv3d weight [Cout][Cin][ntaps]; convT = 1: modes 2 + 3 of an nn.ConvTranspose3d(k2,s2)
+ * weight [Cin][Cout][8] (main.py:121,130,216,219,229,252,258).  Buffers sized as for b3d_pack_weight. */
+int b3d_pack_weight_pair(int convT, const float* w, int Cout, int Cin, int ntaps, void* out_fprop, void* out_dgrad,
+                         void* stream);
 /* nn.Conv3d(k=3,pad=1) main.py:130,216,219 and nn.Conv3d(k=1) main.py:229,252,258 (forward; with mode-1 weights: the
  * data gradient autograd computes for them).  Optional (+=) GroupNorm/BatchNorm partial sums of the output. */
 int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,

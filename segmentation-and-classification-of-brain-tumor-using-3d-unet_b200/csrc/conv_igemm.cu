@@ -488,6 +488,69 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
   }
 }
 
+// Both packed copies of one weight from ONE coalesced read (a training step re-packs every conv weight after the optimizer
+// moved it: 92 M parameters = 370 MB fp32 in, 2 x 185 MB bf16 out).  A block owns a 16 x 16 tile of the two leading source
+// dimensions with all taps: it reads 16 runs of 16*T contiguous floats into shared memory and writes 32-byte runs (16 bf16
+// along K) into each packed layout.  src[(a*B + b)*T + t]:
+//   conv  (a = co, b = ci): fprop[tp][co][ci]                 dgrad[tp][ci][co] holding tap ntaps-1-t   (tp = packed tap order)
+//   convT (a = ci, b = co): fprop[t8*Cout + co][ci]           dgrad[ci][t8*Cout + co]
+template <bool CONVT>
+__global__ void __launch_bounds__(256) pack_pair_kernel(const float* __restrict__ w, bf16* __restrict__ out_f,
+                                                        bf16* __restrict__ out_d, int A, int B, int T, int Kp_f, int rows_f,
+                                                        int Kp_d, int rows_d) {
+  extern __shared__ float tile[];   // [16 a][16 b][T] (+1 pad per a-row to spread banks)
+  const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+  const int run = 16 * T, pitch = run + 1;
+  for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
+    const int al = i / run, r = i - al * run;
+    const int bl = r / T;
+    float v = 0.f;
+    if (a0 + al < A && b0 + bl < B) v = w[((long long)(a0 + al) * B + b0) * T + r];
+    tile[al * pitch + r] = v;
+  }
+  __syncthreads();
+  // work item = (tap, line, half): 8 bf16 = 16 bytes; a line is 16 elements along the packed K index
+  const int items = T * 16 * 2;
+  for (int i = threadIdx.x; i < 2 * items; i += blockDim.x) {
+    const bool second = i >= items;            // false: K runs along b (fprop of conv / dgrad of convT); true: K runs along a
+    int j = second ? i - items : i;
+    const int half = j & 1; j >>= 1;
+    const int line = j & 15; const int tp = j >> 4;
+    float v[8];
+    if (!CONVT) {
+      int t = tp;
+      if (T == 27) t = (tp % 3) * 9 + tp / 3;   // packed tap order (kh,kw,kd) -> reference order (kd,kh,kw)
+      if (!second) {   // fprop[tp][co = a0+line][ci = b0 + 8*half ..]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tile[line * pitch + (8 * half + e) * T + t];
+        const int co = a0 + line, ci = b0 + 8 * half;
+        if (co < rows_f && ci < Kp_f) stg16(out_f + ((long long)tp * rows_f + co) * Kp_f + ci, pack8(v));
+      } else {         // dgrad[tp][ci = b0+line][co = a0 + 8*half ..], tap flipped
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tile[(8 * half + e) * pitch + line * T + (T - 1 - t)];
+        const int ci = b0 + line, co = a0 + 8 * half;
+        if (ci < rows_d && co < Kp_d) stg16(out_d + ((long long)tp * rows_d + ci) * Kp_d + co, pack8(v));
+      }
+    } else {
+      const int Cout = B;
+      if (!second) {   // dgrad[ci = a0+line][k = t8*Cout + co .. 8 consecutive co]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tile[line * pitch + (8 * half + e) * T + tp];
+        const int ci = a0 + line, co = b0 + 8 * half;
+        if (ci < rows_d && co < Cout) {
+          if (co + 8 <= Cout) stg16(out_d + (long long)ci * Kp_d + (long long)tp * Cout + co, pack8(v));
+          else for (int e = 0; e < 8 && co + e < Cout; ++e) out_d[(long long)ci * Kp_d + (long long)tp * Cout + co + e] = __float2bfloat16(v[e]);
+        }
+      } else {         // fprop[row = t8*Cout + co = b0+line][k = ci = a0 + 8*half ..]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = tile[(8 * half + e) * pitch + line * T + tp];
+        const int co = b0 + line, ci = a0 + 8 * half;
+        if (co < Cout && ci < Kp_f) stg16(out_f + ((long long)tp * Cout + co) * Kp_f + ci, pack8(v));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side: planner + launcher
 // ---------------------------------------------------------------------------------------------
@@ -744,6 +807,28 @@ int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void
   const long long total = (long long)ptaps * rows * Kp;
   int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, mode, Cout, Cin, ntaps, Kp, rows); ++g_b3d_launches;
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// Both packed copies of a weight in one launch (modes 0+1 for nn.Conv3d, 2+3 for nn.ConvTranspose3d k2 s2); the layouts
+// are those of b3d_pack_weight.  convT: the dgrad buffer (K = 8*Cout, which need not be a multiple of 16 wide per tap) must be
+// zero-initialised by the caller when 8*Cout < Kp_d (never the case for Cout % 2 == 0).
+int b3d_pack_weight_pair(int convT, const float* w, int Cout, int Cin, int ntaps, void* out_fprop, void* out_dgrad,
+                         void* stream) {
+  B3D_REQUIRE(ntaps >= 1 && ntaps <= 27, "pack_weight_pair: bad ntaps %d", ntaps);
+  const int r16i = (Cin + 15) / 16 * 16, r16o = (Cout + 15) / 16 * 16;
+  const size_t smem = (size_t)16 * (16 * ntaps + 1) * sizeof(float);
+  if (!convT) {
+    dim3 grid(r16i / 16, r16o / 16);   // x: ci tiles (b), y: co tiles (a)
+    pack_pair_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)out_fprop, (bf16*)out_dgrad, Cout, Cin, ntaps,
+                                                                      r16i, r16o, r16o, r16i); ++g_b3d_launches;
+  } else {
+    B3D_REQUIRE(ntaps == 8 && Cout % 8 == 0, "pack_weight_pair: ConvTranspose3d needs 8 taps and Cout %% 8 == 0");
+    dim3 grid((Cout + 15) / 16, r16i / 16);   // x: co tiles (b), y: ci tiles (a)
+    pack_pair_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)out_fprop, (bf16*)out_dgrad, Cin, Cout, 8, r16i,
+                                                                     8 * Cout, 8 * Cout, r16i); ++g_b3d_launches;
+  }
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

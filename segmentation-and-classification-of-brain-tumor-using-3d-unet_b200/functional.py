@@ -11,26 +11,46 @@ import torch
 from . import ops
 
 def packed(param, mode):
-    """bf16 tcgen05-ready copy of a conv weight, cached ON the parameter object until it is modified in place (optimizer
-    step, load_state_dict, .to(device)): validated by the tensor's version counter and storage address.  (A global cache
-    keyed by id(param) is wrong: a new model can reuse the id, the version and — through the caching allocator — even the
-    address of a freed parameter, and would silently get the old model's packed weights.)"""
+    """bf16 tcgen05-ready copy of a conv weight, cached ON the parameter object until the parameter changes.  A cache entry is
+    valid while (a) the tensor's version counter and storage address are unchanged (in-place updates, load_state_dict,
+    .to(device)) and (b) no optimizer stepped since: torch's fused / capturable optimizers update parameters WITHOUT bumping
+    the version counter, so a global optimizer post-step hook (registered at import) advances the cache epoch, as does a
+    replayed CUDA graph (graph.py).  Anything else that writes parameter memory behind autograd's back must call
+    `clear_pack_cache()`.  (A global cache keyed by id(param) is wrong: a new model can reuse the id, the version and —
+    through the caching allocator — even the address of a freed parameter.)
+    Both copies a layer needs (fprop + dgrad) are produced by one launch from one read of the fp32 weight."""
     cache = param.__dict__.setdefault("_b3d_pack", {})
+    key = (param._version, param.data_ptr(), _PACK_EPOCH[0])
     hit = cache.get(mode)
-    if hit is not None and hit[0] == (param._version, param.data_ptr(), _PACK_EPOCH[0]):
+    if hit is not None and hit[0] == key:
         return hit[1], hit[2], hit[3]
-    wp, kp, rows = ops.pack_weight(param, mode)
-    cache[mode] = ((param._version, param.data_ptr(), _PACK_EPOCH[0]), wp, kp, rows)
-    return wp, kp, rows
+    if ops.PAIR_PACK and param.is_cuda:
+        for m, (wp, kp, rows) in ops.pack_weight_pair(param, mode in (ops.PACK_CONVT_FPROP, ops.PACK_CONVT_DGRAD)).items():
+            cache[m] = (key, wp, kp, rows)
+    else:
+        wp, kp, rows = ops.pack_weight(param, mode)
+        cache[mode] = (key, wp, kp, rows)
+    hit = cache[mode]
+    return hit[1], hit[2], hit[3]
 
 
 _PACK_EPOCH = [0]
 
 
 def clear_pack_cache():
-    """Invalidate every cached packed weight.  A replayed CUDA graph (graph.py) updates parameters without touching their
-    Python version counters, so GraphedTrainStep calls this after every replay."""
+    """Invalidate every cached packed weight (see `packed`)."""
     _PACK_EPOCH[0] += 1
+
+
+def _optimizer_stepped(optimizer, args, kwargs):
+    _PACK_EPOCH[0] += 1
+
+
+try:   # every torch optimizer step invalidates the packed weights (fused AdamW does not bump tensor version counters)
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _OPT_HOOK = _reg_hook(_optimizer_stepped)
+except ImportError:   # pragma: no cover - very old torch: fall back to "never cache across calls that enable grad"
+    _OPT_HOOK = None
 
 
 def act_padded(n, d, h, w, c, device):
@@ -57,15 +77,18 @@ def double_conv_fwd(x, p, pre, cin_real, need_bwd):
     w1, w2 = p[pre + "double_conv.0.weight"], p[pre + "double_conv.3.weight"]
     cout = w1.shape[0]
     w1p, _, rows1 = packed(w1, ops.PACK_FPROP)
+    has_res_conv = (pre + "residual.0.weight") in p
+    r = st_r = None
+    if has_res_conv:   # the residual projection only depends on x: a side branch that overlaps with the 3x3x3 convs
+        wrp, _, rowsr = packed(p[pre + "residual.0.weight"], ops.PACK_FPROP)
+        with ops.side_branch(ops.BRANCH_MASK & 1, x) as br:
+            r, st_r = ops.conv_fprop(x, wrp, rowsr, cout, 1, groups=8)
     y1, st1 = ops.conv_fprop(x, w1p, rows1, cout, 3, groups=8)
     a1 = ops.gn_apply(y1, st1, p[pre + "double_conv.1.weight"], p[pre + "double_conv.1.bias"], 8, True)
     w2p, _, rows2 = packed(w2, ops.PACK_FPROP)
     y2, st2 = ops.conv_fprop(a1, w2p, rows2, cout, 3, groups=8)
-    has_res_conv = (pre + "residual.0.weight") in p
-    r = st_r = None
     if has_res_conv:
-        wrp, _, rowsr = packed(p[pre + "residual.0.weight"], ops.PACK_FPROP)
-        r, st_r = ops.conv_fprop(x, wrp, rowsr, cout, 1, groups=8)
+        br.join()
         out = ops.gn_apply(y2, st2, p[pre + "double_conv.4.weight"], p[pre + "double_conv.4.bias"], 8, True, res=r,
                            res_stats=st_r, res_gamma=p[pre + "residual.1.weight"], res_beta=p[pre + "residual.1.bias"],
                            res_groups=8)
@@ -80,6 +103,11 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
     grads = {}
     w1, w2 = p[pre + "double_conv.0.weight"], p[pre + "double_conv.3.weight"]
     cout = w1.shape[0]
+    br = None
+    if r is not None:   # residual-branch GroupNorm backward: independent of the main chain until the final dx add
+        with ops.side_branch(ops.BRANCH_MASK & 4, dout, r) as br:
+            dr, grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = ops.gn_bwd(
+                dout, r, st_r, p[pre + "residual.1.weight"], p[pre + "residual.1.bias"], 8, False)
     # tail: out = relu(GN(y2)) + GN_r(r)
     dy2, grads[pre + "double_conv.4.weight"], grads[pre + "double_conv.4.bias"] = ops.gn_bwd(
         dout, y2, st2, p[pre + "double_conv.4.weight"], p[pre + "double_conv.4.bias"], 8, True)
@@ -96,8 +124,7 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
         dx, _ = ops.conv_fprop(dy1, w1d, rows1d, x.shape[-1], 3)
     del dy1
     if r is not None:
-        dr, grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = ops.gn_bwd(
-            dout, r, st_r, p[pre + "residual.1.weight"], p[pre + "residual.1.bias"], 8, False)
+        br.join()
         grads[pre + "residual.0.weight"] = ops.conv_wgrad(x, dr, cin_real, cout, 1)
         if need_dx:
             wrd, _, rowsrd = packed(p[pre + "residual.0.weight"], ops.PACK_DGRAD)
@@ -291,7 +318,8 @@ def unet_fwd(x_ncdhw, p, bufs, features, training, dropout_masks, need_bwd):
         skips.append(out)
         S["enc"].append(sv)
         if training and i < nl - 1:
-            deep.append(ds_head_fwd(out, p, i, (d, h, w)))
+            with ops.side_branch(ops.BRANCH_MASK & 2, out):
+                deep.append(ds_head_fwd(out, p, i, (d, h, w)))
         mask = dropout_masks[i] if (training and dropout_masks is not None) else None
         x = ops.pool_fwd(out, mask)
         S["pool"].append((out, mask))
@@ -304,6 +332,8 @@ def unet_fwd(x_ncdhw, p, bufs, features, training, dropout_masks, need_bwd):
         x, sv2 = double_conv_fwd(cat, p, "ups.%d." % (3 * j + 2), cat.shape[-1], need_bwd)
         S["dec"].append(sv2)
     logits, S["final"] = final_fwd(x, p, bufs, training, need_bwd)
+    if ops.BRANCH_MASK & 2:
+        ops.wgrad_join()   # the deep-supervision maps were produced on the side stream
     S["skips"] = skips if need_bwd else None
     return logits, deep, (S if need_bwd else None)
 

@@ -97,6 +97,7 @@ def reset_scratch():
 # weights
 # ---------------------------------------------------------------------------------------------------------------
 PACK_FPROP, PACK_DGRAD, PACK_CONVT_FPROP, PACK_CONVT_DGRAD = 0, 1, 2, 3
+PAIR_PACK = True   # functional.packed: produce the fprop and dgrad copies of a weight with one launch
 
 
 def pack_weight(w, mode):
@@ -124,6 +125,29 @@ def pack_weight(w, mode):
     check(_L().b3d_pack_weight(c_int(mode), ptr(w), c_int(cout), c_int(cin), c_int(ntaps), ptr(out), c_int(kp), c_int(rows),
                                stream_ptr()))
     return out, kp, rows
+
+
+def pack_weight_pair(w, conv_transpose):
+    """Both packed copies of one weight in a single launch (one read of the fp32 weight).  Returns
+    {mode: (packed, Kp, rows)} for modes (PACK_FPROP, PACK_DGRAD) or (PACK_CONVT_FPROP, PACK_CONVT_DGRAD)."""
+    w = w.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    dev = w.device
+    if not conv_transpose:
+        cout, cin = w.shape[0], w.shape[1]
+        ntaps = w.shape[2] * w.shape[3] * w.shape[4]
+        ri, ro = roundup(cin, 16), roundup(cout, 16)
+        of = torch.empty(ntaps * ro * ri, dtype=torch.bfloat16, device=dev)
+        od = torch.empty(ntaps * ri * ro, dtype=torch.bfloat16, device=dev)
+        check(_L().b3d_pack_weight_pair(c_int(0), ptr(w), c_int(cout), c_int(cin), c_int(ntaps), ptr(of), ptr(od), stream_ptr()))
+        return {PACK_FPROP: (of, ri, ro), PACK_DGRAD: (od, ro, ri)}
+    cin, cout = w.shape[0], w.shape[1]
+    ri = roundup(cin, 16)
+    of = torch.empty(8 * cout * ri, dtype=torch.bfloat16, device=dev)
+    od = torch.empty(ri * 8 * cout, dtype=torch.bfloat16, device=dev)
+    check(_L().b3d_pack_weight_pair(c_int(1), ptr(w), c_int(cout), c_int(cin), c_int(8), ptr(of), ptr(od), stream_ptr()))
+    return {PACK_CONVT_FPROP: (of, ri, 8 * cout), PACK_CONVT_DGRAD: (od, 8 * cout, ri)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -210,6 +234,45 @@ class _wgrad_ctx:
             for t in self.inputs:
                 t.record_stream(self.s)
         return False
+
+
+# Independent HBM-bound branches (the residual 1x1x1 conv + its GroupNorm backward, the deep-supervision heads) can ride the
+# same side stream so that they overlap with the tensor-bound 3x3x3 kernels of the main chain.  B3D_BRANCH_STREAM selects
+# which: bit 0 = forward residual conv, bit 1 = forward deep-supervision heads, bit 2 = backward residual GroupNorm.
+BRANCH_MASK = int(_os.environ.get("B3D_BRANCH_STREAM", "0"))
+
+
+class side_branch:
+    """with side_branch(enabled, inputs...) as br: <enqueue the branch> ; later br.join() before the main stream reads its
+    results.  A no-op context when disabled (or when the side stream is switched off)."""
+
+    def __init__(self, enabled, *inputs):
+        self.on = bool(enabled) and WGRAD_SIDE
+        self.inputs = inputs
+        self.event = None
+
+    def __enter__(self):
+        global WGRAD_STREAM
+        if self.on:
+            if WGRAD_STREAM is None:
+                WGRAD_STREAM = torch.cuda.Stream()
+            WGRAD_STREAM.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(WGRAD_STREAM)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.event = WGRAD_STREAM.record_event()
+            self.ctx.__exit__(*exc)
+            for t in self.inputs:
+                if t is not None:
+                    t.record_stream(WGRAD_STREAM)
+        return False
+
+    def join(self):
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
 
 
 def wgrad_join():

@@ -380,3 +380,19 @@ def test_conv_wgrad_mn_major(n, d, h, w, cin, cout):
     ref = wt.grad
     err = (dw - ref).abs().max().item()
     assert err <= 2e-3 * ref.abs().max().item() + 1e-3, "max err %g vs scale %g" % (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("shape,convt", [
+    ((32, 32, 3, 3, 3), False), ((32, 4, 3, 3, 3), False), ((16, 32, 3, 3, 3), False), ((4, 16, 1, 1, 1), False),
+    ((64, 32, 1, 1, 1), False), ((24, 40, 3, 3, 3), False), ((256, 128, 3, 3, 3), False), ((1, 8, 1, 1, 1), False),
+    ((64, 32, 2, 2, 2), True), ((32, 16, 2, 2, 2), True), ((512, 256, 2, 2, 2), True), ((24, 8, 2, 2, 2), True),
+])
+def test_pack_weight_pair_matches_single_packs(shape, convt):
+    """The one-read pair pack (what a training step runs for every conv weight) is bit-identical to the per-mode packs."""
+    g = torch.Generator().manual_seed(41)
+    w = torch.randn(*shape, generator=g).to(DEV)
+    pair = ops.pack_weight_pair(w, convt)
+    for mode, (wp, kp, rows) in pair.items():
+        ref, kp_r, rows_r = ops.pack_weight(w, mode)
+        assert (kp, rows) == (kp_r, rows_r)
+        assert wp.shape == ref.shape and torch.equal(wp, ref), "mode %d differs" % mode

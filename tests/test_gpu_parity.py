@@ -282,7 +282,10 @@ def test_graphed_train_step_matches_eager():
             # the capture protocol runs 3 warm-up optimizer steps: undo them so that both runs start from the same weights
             step = U.GraphedTrainStep(model, crit, opt, xd, yd, warmup=1)
             model.load_state_dict(sd)
-            opt.state.clear()
+            for st in opt.state.values():      # the graph captured the state tensors by address: reset them in place
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
             for _ in range(3):
                 out.append(float(step(xd, yd)))
         else:
@@ -294,9 +297,32 @@ def test_graphed_train_step_matches_eager():
                 out.append(float(loss))
         losses[mode] = out
     e, g = losses["eager"], losses["graph"]
-    assert abs(e[0] - g[0]) <= 2e-3 * abs(e[0]), (e, g)          # same weights, same batch: first losses agree (bf16 jitter)
     assert e[2] < e[0] and g[2] < g[0], (e, g)                    # both actually train
-    assert abs(e[2] - g[2]) <= 5e-2 * abs(e[2]), (e, g)
+    for a, b in zip(e, g):                                        # same kernels in the same order: only fp32-atomic jitter
+        assert abs(a - b) <= 2e-4 * abs(a), (e, g)
+
+
+def test_optimizer_step_invalidates_packed_weights():
+    """torch's fused AdamW updates parameters without bumping their version counters; the bf16 packed copies the kernels
+    read must follow anyway (global optimizer post-step hook -> cache epoch).  After a step the model must compute exactly
+    what a freshly constructed model with the updated state_dict computes."""
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(4, 4, feats, seed=9)
+    x, y = O.make_inputs(1, 32, 32, 32, seed=9)
+    xd, yd = x.to(DEV), y.to(DEV)
+    model = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), sd).train()
+    crit = U.DeepSupervisionLoss3D()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=1e-4, fused=True)
+    before = model(xd)[0].detach().clone()
+    opt.zero_grad(set_to_none=True)
+    crit(model(xd), yd).backward()
+    opt.step()
+    after = model(xd)[0].detach().clone()
+    fresh = _load(U.UNet3D(4, 4, features=list(feats), dropout_rate=0.0), {k: v.detach().clone() for k, v in model.state_dict().items()}).train()
+    # BatchNorm running statistics were advanced by the forwards above; train mode normalises with batch statistics
+    want = fresh(xd)[0].detach()
+    assert not torch.equal(before, after), "the optimizer step did not change the forward pass"
+    assert torch.equal(after, want), "forward after opt.step() differs from a fresh model with the same parameters (stale packed weights): max |d| = %g" % float((after - want).abs().max())
 
 
 def test_packed_weight_cache_is_per_parameter():
