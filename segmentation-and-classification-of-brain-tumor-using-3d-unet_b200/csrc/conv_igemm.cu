@@ -501,12 +501,23 @@ __global__ void __launch_bounds__(256) pack_pair_kernel(const float* __restrict_
   extern __shared__ float tile[];   // [16 a][16 b][T] (+1 pad per a-row to spread banks)
   const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
   const int run = 16 * T, pitch = run + 1;
-  for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
-    const int al = i / run, r = i - al * run;
-    const int bl = r / T;
-    float v = 0.f;
-    if (a0 + al < A && b0 + bl < B) v = w[((long long)(a0 + al) * B + b0) * T + r];
-    tile[al * pitch + r] = v;
+  if (b0 + 16 <= B && ((long long)B * T) % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {   // whole, 16-byte aligned runs
+    const int run4 = run / 4;
+    for (int i = threadIdx.x; i < 16 * run4; i += blockDim.x) {
+      const int al = i / run4, r4 = i - al * run4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a0 + al < A) v = __ldg(reinterpret_cast<const float4*>(w + ((long long)(a0 + al) * B + b0) * T) + r4);
+      float* d = tile + al * pitch + 4 * r4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
+      const int al = i / run, r = i - al * run;
+      const int bl = r / T;
+      float v = 0.f;
+      if (a0 + al < A && b0 + bl < B) v = w[((long long)(a0 + al) * B + b0) * T + r];
+      tile[al * pitch + r] = v;
+    }
   }
   __syncthreads();
   // work item = (tap, line, half): 8 bf16 = 16 bytes; a line is 16 elements along the packed K index
