@@ -101,7 +101,8 @@ def test_convT2_fprop_and_dgrad():
     _close_bf16(dx, refdx)
 
 
-@pytest.mark.parametrize("c,groups,relu,res", [(32, 8, True, 0), (64, 8, True, 1), (16, 4, False, 0), (256, 8, True, 1)])
+@pytest.mark.parametrize("c,groups,relu,res", [(32, 8, True, 0), (64, 8, True, 1), (16, 4, False, 0), (256, 8, True, 1),
+                                               (2048, 8, True, 0)])   # wide model's concat width: > 48 KB of dynamic smem
 def test_groupnorm_fwd_bwd(c, groups, relu, res):
     n, s = 2, 8
     y = _bf(n, s, s, s, c, seed=10, scale=2.0)
