@@ -66,6 +66,12 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
 int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const double* stats,
                      const float* gamma, const float* beta, int G, int relu, const double* sums, void* dx,
                      long long lddx, int accumulate, int N, long long V, int C, float eps, void* stream);
+/* dual backward of a residual block's tail  out = relu(GN_a(ya)) + GN_b(yb)  (main.py:238-240): one pass over dy for both
+ * branches.  Returns 1 without launching when the shape does not suit it (use the two calls above per branch). */
+int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ldya, const double* stats_a,
+                    const float* gamma_a, const float* beta_a, const void* yb, long long ldyb, const double* stats_b,
+                    const float* gamma_b, int G, double* sums_a, double* sums_b, void* dxa, long long lddxa, void* dxb,
+                    long long lddxb, int N, long long V, int C, float eps, void* stream);
 int b3d_gn_param_grad(const double* sums, int N, int C, float* dgamma, float* dbeta, int accumulate, void* stream);
 int b3d_add_bf16(const void* a, long long lda, const void* b, long long ldb, void* o, long long ldo, long long V, int C,
                  void* stream);

@@ -293,6 +293,171 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Dual GroupNorm backward of a residual block's tail:  out = relu(GN_a(ya)) + GN_b(yb)   (main.py:238-240)
+// Both branches receive the same upstream gradient dy; the separate kernels read it four times (2 x reduce, 2 x apply), the
+// dual ones twice: 8 instead of 10 tensor passes per block.  Fixed 8-channel chunk per thread (blockDim % (C/8) == 0),
+// algebraically folded per-channel coefficients so that both branches' constants fit in registers:
+//   x̂ = x*ka + kb ;  relu test: x*S + T <= 0 ;  dx = dz*P - Q - x*R   with P = γ*rstd, R = ka*Cg, Q = Bg + kb*Cg
+//   (Bg, Cg = rstd * mean_g(γ·Σdz), rstd * mean_g(γ·Σdz·x̂): the group terms of the standard formula).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_dual_reduce_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ ya, long long ldya, const double* __restrict__ stats_a,
+    const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const bf16* __restrict__ yb, long long ldyb,
+    const double* __restrict__ stats_b, int G, double* __restrict__ sums_a, double* __restrict__ sums_b, long long V, int C,
+    float eps) {
+  extern __shared__ float sm[];
+  float* c_ka = sm; float* c_kb = sm + C; float* c_S = sm + 2 * C; float* c_T = sm + 3 * C;
+  float* c_kab = sm + 4 * C; float* c_kbb = sm + 5 * C;
+  double* red = reinterpret_cast<double*>(sm + 6 * C);   // [4][C]: Σdz_a, Σdz_a·x̂a, Σdy, Σdy·x̂b
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd(stats_a, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    c_ka[c] = rstd; c_kb[c] = -mean * rstd;
+    { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }   // the forward's own expression (gn_apply_kernel)
+    gn_mean_rstd(stats_b, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    c_kab[c] = rstd; c_kbb[c] = -mean * rstd;
+    red[c] = 0.0; red[C + c] = 0.0; red[2 * C + c] = 0.0; red[3 * C + c] = 0.0;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int c0 = (int)(threadIdx.x % C8) * 8;
+  const bf16* dyn = dy + (long long)n * V * lddy;
+  const bf16* yan = ya + (long long)n * V * ldya;
+  const bf16* ybn = yb + (long long)n * V * ldyb;
+  float ka[8], kb[8], kS[8], kT[8], kab[8], kbb[8], a1[8], a2[8], a3[8], a4[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ka[j] = c_ka[c0 + j]; kb[j] = c_kb[c0 + j]; kS[j] = c_S[c0 + j]; kT[j] = c_T[c0 + j];
+    kab[j] = c_kab[c0 + j]; kbb[j] = c_kbb[c0 + j];
+    a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; a4[j] = 0.f;
+  }
+  const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+  long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+  for (; vox < V; vox += 2 * vstep) {
+    const bool two = vox + vstep < V;
+    const long long vox2 = two ? vox + vstep : vox;
+    const uint4 ud = ldg16_stream(dyn + vox * lddy + c0), ua = ldg16_stream(yan + vox * ldya + c0), ub = ldg16_stream(ybn + vox * ldyb + c0);
+    const uint4 ud2 = ldg16_stream(dyn + vox2 * lddy + c0), ua2 = ldg16_stream(yan + vox2 * ldya + c0), ub2 = ldg16_stream(ybn + vox2 * ldyb + c0);
+    float d[8], x[8], z[8];
+    unpack8(ud, d); unpack8(ua, x); unpack8(ub, z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dz = (fmaf(x[j], kS[j], kT[j]) <= 0.f) ? 0.f : d[j];
+      a1[j] += dz; a2[j] = fmaf(dz, fmaf(x[j], ka[j], kb[j]), a2[j]);
+      a3[j] += d[j]; a4[j] = fmaf(d[j], fmaf(z[j], kab[j], kbb[j]), a4[j]);
+    }
+    if (two) {
+      unpack8(ud2, d); unpack8(ua2, x); unpack8(ub2, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dz = (fmaf(x[j], kS[j], kT[j]) <= 0.f) ? 0.f : d[j];
+        a1[j] += dz; a2[j] = fmaf(dz, fmaf(x[j], ka[j], kb[j]), a2[j]);
+        a3[j] += d[j]; a4[j] = fmaf(d[j], fmaf(z[j], kab[j], kbb[j]), a4[j]);
+      }
+    }
+  }
+  const int grp = C8 < 32 ? C8 : 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a1[j] = warp_sum_mod(a1[j], grp); a2[j] = warp_sum_mod(a2[j], grp);
+    a3[j] = warp_sum_mod(a3[j], grp); a4[j] = warp_sum_mod(a4[j], grp);
+  }
+  if ((int)(threadIdx.x & 31) < grp) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[c0 + j], (double)a1[j]); atomicAdd(&red[C + c0 + j], (double)a2[j]);
+      atomicAdd(&red[2 * C + c0 + j], (double)a3[j]); atomicAdd(&red[3 * C + c0 + j], (double)a4[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&sums_a[((long long)n * C + c) * 2], red[c]);
+    atomicAdd(&sums_a[((long long)n * C + c) * 2 + 1], red[C + c]);
+    atomicAdd(&sums_b[((long long)n * C + c) * 2], red[2 * C + c]);
+    atomicAdd(&sums_b[((long long)n * C + c) * 2 + 1], red[3 * C + c]);
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_dual_apply_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ ya, long long ldya, const double* __restrict__ stats_a,
+    const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const double* __restrict__ sums_a,
+    const bf16* __restrict__ yb, long long ldyb, const double* __restrict__ stats_b, const float* __restrict__ gamma_b,
+    const double* __restrict__ sums_b, int G, bf16* __restrict__ dxa, long long lddxa, bf16* __restrict__ dxb, long long lddxb,
+    long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* c_S = sm; float* c_T = sm + C; float* c_Pa = sm + 2 * C; float* c_Qa = sm + 3 * C; float* c_Ra = sm + 4 * C;
+  float* c_Pb = sm + 5 * C; float* c_Qb = sm + 6 * C; float* c_Rb = sm + 7 * C;
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const double m = (double)cpg * (double)V;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float mean, rstd;
+    gn_mean_rstd(stats_a, n, G, g, m, eps, mean, rstd);
+    double sb = 0, sc2 = 0;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+      sb += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2];
+      sc2 += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2 + 1];
+    }
+    float Bg = (float)(sb / m) * rstd, Cg = (float)(sc2 / m) * rstd, kb = -mean * rstd;
+    { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }   // the forward's own expression
+    c_Pa[c] = gamma_a[c] * rstd; c_Qa[c] = fmaf(kb, Cg, Bg); c_Ra[c] = rstd * Cg;
+    gn_mean_rstd(stats_b, n, G, g, m, eps, mean, rstd);
+    sb = 0; sc2 = 0;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+      sb += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2];
+      sc2 += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2 + 1];
+    }
+    Bg = (float)(sb / m) * rstd; Cg = (float)(sc2 / m) * rstd; kb = -mean * rstd;
+    c_Pb[c] = gamma_b[c] * rstd; c_Qb[c] = fmaf(kb, Cg, Bg); c_Rb[c] = rstd * Cg;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int c0 = (int)(threadIdx.x % C8) * 8;
+  const bf16* dyn = dy + (long long)n * V * lddy;
+  const bf16* yan = ya + (long long)n * V * ldya;
+  const bf16* ybn = yb + (long long)n * V * ldyb;
+  bf16* dxan = dxa + (long long)n * V * lddxa;
+  bf16* dxbn = dxb + (long long)n * V * lddxb;
+  float kS[8], kT[8], Pa[8], Qa[8], Ra[8], Pb[8], Qb[8], Rb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    kS[j] = c_S[c0 + j]; kT[j] = c_T[c0 + j]; Pa[j] = c_Pa[c0 + j]; Qa[j] = c_Qa[c0 + j]; Ra[j] = c_Ra[c0 + j];
+    Pb[j] = c_Pb[c0 + j]; Qb[j] = c_Qb[c0 + j]; Rb[j] = c_Rb[c0 + j];
+  }
+  const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+  long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+  for (; vox < V; vox += 2 * vstep) {
+    const bool two = vox + vstep < V;
+    const long long vox2 = two ? vox + vstep : vox;
+    const uint4 ud = ldg16_stream(dyn + vox * lddy + c0), ua = ldg16_stream(yan + vox * ldya + c0), ub = ldg16_stream(ybn + vox * ldyb + c0);
+    const uint4 ud2 = ldg16_stream(dyn + vox2 * lddy + c0), ua2 = ldg16_stream(yan + vox2 * ldya + c0), ub2 = ldg16_stream(ybn + vox2 * ldyb + c0);
+    float d[8], x[8], z[8], oa[8], ob[8];
+    unpack8(ud, d); unpack8(ua, x); unpack8(ub, z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dz = (fmaf(x[j], kS[j], kT[j]) <= 0.f) ? 0.f : d[j];
+      oa[j] = fmaf(dz, Pa[j], -fmaf(x[j], Ra[j], Qa[j]));
+      ob[j] = fmaf(d[j], Pb[j], -fmaf(z[j], Rb[j], Qb[j]));
+    }
+    stg16(dxan + vox * lddxa + c0, pack8(oa));
+    stg16(dxbn + vox * lddxb + c0, pack8(ob));
+    if (two) {
+      unpack8(ud2, d); unpack8(ua2, x); unpack8(ub2, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dz = (fmaf(x[j], kS[j], kT[j]) <= 0.f) ? 0.f : d[j];
+        oa[j] = fmaf(dz, Pa[j], -fmaf(x[j], Ra[j], Qa[j]));
+        ob[j] = fmaf(d[j], Pb[j], -fmaf(z[j], Rb[j], Qb[j]));
+      }
+      stg16(dxan + vox2 * lddxa + c0, pack8(oa));
+      stg16(dxbn + vox2 * lddxb + c0, pack8(ob));
+    }
+  }
+}
+
 // dgamma[c] = Σ_n sums[n][c][1], dbeta[c] = Σ_n sums[n][c][0]
 __global__ void gn_param_grad_kernel(const double* __restrict__ sums, int N, int C, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int accumulate) {
@@ -385,6 +550,29 @@ int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ld
   if (relu) { if (accumulate) LAUNCH(true, true); else LAUNCH(true, false); }
   else { if (accumulate) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// Dual backward of  out = relu(GN_a(ya)) + GN_b(yb)  w.r.t. ya and yb (both branches see dy).  sums_a / sums_b: zeroed
+// double [N][C][2], left holding (Σdz, Σdz·x̂) per channel for b3d_gn_param_grad.  Returns 1 (nothing launched) when the
+// shape does not suit the fixed-chunk kernels — the caller then uses b3d_gn_bwd_reduce / b3d_gn_bwd_apply per branch.
+int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ldya, const double* stats_a,
+                    const float* gamma_a, const float* beta_a, const void* yb, long long ldyb, const double* stats_b,
+                    const float* gamma_b, int G, double* sums_a, double* sums_b, void* dxa, long long lddxa, void* dxb,
+                    long long lddxb, int N, long long V, int C, float eps, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && C % G == 0, "gn_bwd_dual: bad C=%d G=%d", C, G);
+  const int C8 = C / 8;
+  if (C > 512 || (GN_THREADS % C8) != 0) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per_sample = std::max(1, std::min(ew_blocks(V * C8, GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
+  gn_bwd_dual_reduce_kernel<<<dim3(per_sample, N), GN_THREADS, (6 * (size_t)C) * sizeof(float) + 4 * (size_t)C * sizeof(double), st>>>(
+      (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, (const bf16*)yb, ldyb, stats_b, G, sums_a, sums_b,
+      V, C, eps); ++g_b3d_launches;
+  B3D_CHECK_CUDA(cudaGetLastError());
+  gn_bwd_dual_apply_kernel<<<dim3(ew_blocks(V * C8, GN_THREADS * 2), N), GN_THREADS, 8 * (size_t)C * sizeof(float), st>>>(
+      (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, sums_a, (const bf16*)yb, ldyb, stats_b, gamma_b,
+      sums_b, G, (bf16*)dxa, lddxa, (bf16*)dxb, lddxb, V, C, eps); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

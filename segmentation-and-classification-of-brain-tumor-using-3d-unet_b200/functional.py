@@ -103,14 +103,20 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
     grads = {}
     w1, w2 = p[pre + "double_conv.0.weight"], p[pre + "double_conv.3.weight"]
     cout = w1.shape[0]
+    # tail: out = relu(GN(y2)) + GN_r(r).  Both branches see dout: one dual kernel pair reads it once per phase.
     br = None
-    if r is not None:   # residual-branch GroupNorm backward: independent of the main chain until the final dx add
-        with ops.side_branch(ops.BRANCH_MASK & 4, dout, r) as br:
-            dr, grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = ops.gn_bwd(
-                dout, r, st_r, p[pre + "residual.1.weight"], p[pre + "residual.1.bias"], 8, False)
-    # tail: out = relu(GN(y2)) + GN_r(r)
-    dy2, grads[pre + "double_conv.4.weight"], grads[pre + "double_conv.4.bias"] = ops.gn_bwd(
-        dout, y2, st2, p[pre + "double_conv.4.weight"], p[pre + "double_conv.4.bias"], 8, True)
+    dual = ops.gn_bwd_dual(dout, y2, st2, p[pre + "double_conv.4.weight"], p[pre + "double_conv.4.bias"], r, st_r,
+                           p[pre + "residual.1.weight"], 8) if r is not None else None
+    if dual is not None:
+        (dy2, grads[pre + "double_conv.4.weight"], grads[pre + "double_conv.4.bias"],
+         dr, grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"]) = dual
+    else:
+        if r is not None:   # residual-branch GroupNorm backward: independent of the main chain until the final dx add
+            with ops.side_branch(ops.BRANCH_MASK & 4, dout, r) as br:
+                dr, grads[pre + "residual.1.weight"], grads[pre + "residual.1.bias"] = ops.gn_bwd(
+                    dout, r, st_r, p[pre + "residual.1.weight"], p[pre + "residual.1.bias"], 8, False)
+        dy2, grads[pre + "double_conv.4.weight"], grads[pre + "double_conv.4.bias"] = ops.gn_bwd(
+            dout, y2, st2, p[pre + "double_conv.4.weight"], p[pre + "double_conv.4.bias"], 8, True)
     grads[pre + "double_conv.3.weight"] = ops.conv_wgrad(a1, dy2, cout, cout, 3)
     w2d, _, rows2d = packed(w2, ops.PACK_DGRAD)
     da1, _ = ops.conv_fprop(dy2, w2d, rows2d, cout, 3)
@@ -124,7 +130,8 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
         dx, _ = ops.conv_fprop(dy1, w1d, rows1d, x.shape[-1], 3)
     del dy1
     if r is not None:
-        br.join()
+        if br is not None:
+            br.join()
         grads[pre + "residual.0.weight"] = ops.conv_wgrad(x, dr, cin_real, cout, 1)
         if need_dx:
             wrd, _, rowsrd = packed(p[pre + "residual.0.weight"], ops.PACK_DGRAD)

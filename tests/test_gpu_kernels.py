@@ -397,3 +397,31 @@ def test_pack_weight_pair_matches_single_packs(shape, convt):
         ref, kp_r, rows_r = ops.pack_weight(w, mode)
         assert (kp, rows) == (kp_r, rows_r)
         assert wp.shape == ref.shape and torch.equal(wp, ref), "mode %d differs" % mode
+
+
+@pytest.mark.parametrize("c,s", [(32, 8), (16, 8), (256, 4), (512, 2)])
+def test_groupnorm_dual_backward(c, s):
+    """Dual backward of out = relu(GN_a(ya)) + GN_b(yb) (the tail of every residual block): against torch autograd and
+    against the two single-branch kernels."""
+    n, groups = 2, 8
+    ya = _bf(n, s, s, s, c, seed=51, scale=2.0)
+    yb = _bf(n, s, s, s, c, seed=52, scale=1.5)
+    dout = _bf(n, s, s, s, c, seed=53)
+    ga, ba = 1 + 0.2 * torch.randn(c, device=DEV), 0.2 * torch.randn(c, device=DEV)
+    gb, bb = 1 + 0.2 * torch.randn(c, device=DEV), 0.2 * torch.randn(c, device=DEV)
+    sta, stb = _stats(ya, groups), _stats(yb, groups)
+    got = ops.gn_bwd_dual(dout, ya, sta, ga, ba, yb, stb, gb, groups)
+    assert got is not None
+    dxa, dga, dba, dxb, dgb, dbb = got
+    yat, ybt = _ncdhw(ya).requires_grad_(True), _ncdhw(yb).requires_grad_(True)
+    gat, bat, gbt, bbt = [t.clone().requires_grad_(True) for t in (ga, ba, gb, bb)]
+    ref = F.relu(F.group_norm(yat, groups, gat, bat, 1e-5)) + F.group_norm(ybt, groups, gbt, bbt, 1e-5)
+    ref.backward(_ncdhw(dout))
+    _close_bf16(dxa, _ndhwc(yat.grad), tol=1.0 / 32)
+    _close_bf16(dxb, _ndhwc(ybt.grad), tol=1.0 / 32)
+    for a, b in ((dga, gat.grad), (dba, bat.grad), (dgb, gbt.grad), (dbb, bbt.grad)):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-2, atol=2e-2 * b.abs().max().item())
+    sxa, sga, sba = ops.gn_bwd(dout, ya, sta, ga, ba, groups, True)
+    sxb, sgb, sbb = ops.gn_bwd(dout, yb, stb, gb, bb, groups, False)
+    _close_bf16(dxa, sxa.float(), tol=1.0 / 64)
+    _close_bf16(dxb, sxb.float(), tol=1.0 / 64)

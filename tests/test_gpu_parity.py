@@ -437,3 +437,27 @@ def test_training_trajectory_follows_the_oracle(fused):
     for i, (a, b) in enumerate(zip(ref, got)):                  # bf16 activations: 1.5 % per step, like the single-step bar
         assert abs(a - b) <= 1.5e-2 * abs(a), "step %d: oracle %s vs b200 %s" % (i, ref, got)
     assert (ref[0] - got[-1]) >= 0.7 * (ref[0] - ref[-1]), "b200 path trains slower than the oracle: %s vs %s" % (got, ref)
+
+
+def test_single_channel_input_vs_oracle():
+    """The reference's own constructor default and inference call site build `UNet3D(in_channels=1)` (main.py:105,336,
+    web_training.py:67): one real input channel padded to 16 in the staged activation, weight gradient of the first conv
+    cut back to one channel."""
+    feats = (16, 32, 64, 128, 256)
+    sd = O.make_state_dict(1, 4, feats, seed=17)
+    x, y = O.make_inputs(2, 32, 32, 32, in_channels=1, seed=17)
+    model = _load(U.UNet3D(in_channels=1, out_channels=4, features=list(feats), dropout_rate=0.0), sd)
+    model.eval()
+    with torch.no_grad():
+        ev = model(x.to(DEV))
+    rev, _, _ = O.unet_forward(x, sd, feats, training=False)
+    assert ev.shape == rev.shape and _rel_l2(ev.cpu(), rev) <= 2.5e-2
+    model.train()
+    main, deep = model(x.to(DEV))
+    loss = U.DeepSupervisionLoss3D()((main, deep), y.to(DEV))
+    loss.backward()
+    rmain, rdeep, rloss, rgrads, _ = _oracle_train(sd, x, y, feats)
+    assert _rel_l2(main.detach().cpu(), rmain) <= 2.5e-2
+    assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss)
+    assert model.downs[0].double_conv[0].weight.grad.shape == (16, 1, 3, 3, 3)
+    _check_grads(model, rgrads, "cin1", _oracle_autocast_grads(sd, x, y, feats))
