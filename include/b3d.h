@@ -79,6 +79,11 @@ int b3d_add_bf16(const void* a, long long lda, const void* b, long long ldb, voi
 /* ---- MaxPool3d(2,2)+Dropout3d main.py:109-110,173-174 ; input staging training.py:287 (pool_layout.cu) ------- */
 int b3d_pool_fwd(const void* x, long long ldx, const float* mask, void* out, long long ldo, int N, int D, int H, int W,
                  int C, void* stream);
+/* BrainTumorClassifier.features (main.py:305-316): MaxPool3d(2)(ReLU(x)) and AdaptiveAvgPool3d((OD,OH,OW))(ReLU(x)) with the
+ * result in fp32 NCDHW flatten order (what `x.view(x.size(0), -1)`, main.py:326, feeds the Linear layers) */
+int b3d_relu_pool_fwd(const void* x, long long ldx, void* out, long long ldo, int N, int D, int H, int W, int C, void* stream);
+int b3d_relu_adaptive_avgpool(const void* x, long long ldx, float* out, int N, int D, int H, int W, int C, int OD, int OH,
+                              int OW, int relu, void* stream);
 int b3d_pool_bwd(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
                  long long lddx, int accumulate, int N, int D, int H, int W, int C, void* stream);
 int b3d_to_ndhwc_bf16(const float* x, void* out, long long ldo, int N, int Cin, long long V, int Cpad, void* stream);

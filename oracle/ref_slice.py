@@ -37,7 +37,7 @@ def load():
     DeepSupervisionLoss3D (losses.py), CombinedLoss, DiceLoss, FocalLoss (training.py) and calculate_dice_score."""
     ns = {"torch": torch, "nn": nn, "F": F, "np": np}
     main_src = open(os.path.join(REF, "main.py")).read()
-    for cls in ("DoubleConv3D", "AttentionGate3D", "UNet3D"):
+    for cls in ("DoubleConv3D", "AttentionGate3D", "UNet3D", "BrainTumorClassifier"):
         exec(compile(_class_block(main_src, cls), "main.py:" + cls, "exec"), ns)
     tr_src = open(os.path.join(REF, "training.py")).read()
     for cls in ("DiceLoss", "FocalLoss", "CombinedLoss"):

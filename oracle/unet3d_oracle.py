@@ -287,3 +287,42 @@ def voxel_counts(mask, num_classes=4):
     tumour = int((mask > 0).sum())
     per_slice = [(int((mask[:, :, z] > 0).sum())) for z in range(mask.shape[2])]
     return tumour, per_class, per_slice
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BrainTumorClassifier (main.py:301-328; call site classify_tumor main.py:398-425): eval-mode forward only — the reference
+# never trains it.  Conv3d(4,32,3,1,1) ReLU MaxPool3d(2) Conv3d(32,64) ReLU MaxPool3d(2) Conv3d(64,128) ReLU
+# AdaptiveAvgPool3d(4) flatten Linear(8192,512) ReLU Dropout(0.5) Linear(512,num_classes)
+# ---------------------------------------------------------------------------------------------------------------------
+def classifier_param_shapes(num_classes=4):
+    return [("features.0.weight", (32, 4, 3, 3, 3)), ("features.0.bias", (32,)),
+            ("features.3.weight", (64, 32, 3, 3, 3)), ("features.3.bias", (64,)),
+            ("features.6.weight", (128, 64, 3, 3, 3)), ("features.6.bias", (128,)),
+            ("classifier.0.weight", (512, 128 * 4 * 4 * 4)), ("classifier.0.bias", (512,)),
+            ("classifier.3.weight", (num_classes, 512)), ("classifier.3.bias", (num_classes,))]
+
+
+def make_classifier_state_dict(num_classes=4, seed=0, dtype=torch.float32):
+    """Deterministic, reference-independent weights (own generator per tensor; Kaiming-like scales, small biases)."""
+    sd = {}
+    for idx, (key, shape) in enumerate(classifier_param_shapes(num_classes)):
+        g = torch.Generator().manual_seed(seed * 100003 + 5000 + idx)
+        if len(shape) == 5:
+            std = math.sqrt(2.0 / (shape[1] * 27))
+        elif len(shape) == 2:
+            std = math.sqrt(2.0 / shape[1])
+        else:
+            std = 0.1
+        sd[key] = (torch.randn(shape, generator=g, dtype=torch.float64) * std).to(dtype)
+    return sd
+
+
+def classifier_forward(x, sd):
+    """main.py:324-328 in eval mode (Dropout is the identity).  x: [N,4,D,H,W] -> logits [N,num_classes]."""
+    x = F.max_pool3d(F.relu(F.conv3d(x, sd["features.0.weight"], sd["features.0.bias"], padding=1)), 2)
+    x = F.max_pool3d(F.relu(F.conv3d(x, sd["features.3.weight"], sd["features.3.bias"], padding=1)), 2)
+    x = F.relu(F.conv3d(x, sd["features.6.weight"], sd["features.6.bias"], padding=1))
+    x = F.adaptive_avg_pool3d(x, (4, 4, 4))
+    x = x.reshape(x.shape[0], -1)
+    x = F.relu(F.linear(x, sd["classifier.0.weight"], sd["classifier.0.bias"]))
+    return F.linear(x, sd["classifier.3.weight"], sd["classifier.3.bias"])

@@ -18,7 +18,7 @@ static int ew_blocks2(long long total, int threads) {
 
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ mask,
                                                        bf16* __restrict__ out, long long ldo, int N, int D, int H, int W,
-                                                       int C) {
+                                                       int C, int relu) {
   const int C8 = C >> 3;
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Do * Ho * Wo * C8;
@@ -43,12 +43,69 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const bf16* __restrict__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
         }
+    if (relu) {   // MaxPool(ReLU(x)) = ReLU(MaxPool(x))  (BrainTumorClassifier, main.py:307-312)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], 0.f);
+    }
     if (mask) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] *= mask[(long long)n * C + c0 + j];
     }
     const long long ovox = (((long long)n * Do + zo) * Ho + yo) * Wo + xo;
     stg16(out + ovox * ldo + c0, pack8(m));
+  }
+}
+
+// AdaptiveAvgPool3d over NDHWC bf16 (optionally of ReLU(x)): one block per (n, output cell); a thread owns an 8-channel chunk
+// and a slice of the window's voxels; partial sums are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) relu_adaptive_avgpool_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out,
+                                                                    int D, int H, int W, int C, int OD, int OH, int OW, int relu) {
+  __shared__ float part[256 * 8];
+  const int n = blockIdx.y;
+  int o = blockIdx.x;
+  const int ox = o % OW; o /= OW;
+  const int oy = o % OH; const int oz = o / OH;
+  const int z0 = (oz * D) / OD, z1 = ((oz + 1) * D + OD - 1) / OD;
+  const int y0 = (oy * H) / OH, y1 = ((oy + 1) * H + OH - 1) / OH;
+  const int x0 = (ox * W) / OW, x1 = ((ox + 1) * W + OW - 1) / OW;
+  const int wz = z1 - z0, wy = y1 - y0, wx = x1 - x0;
+  const int nvox = wz * wy * wx;
+  const int C8 = C >> 3;
+  for (int cb = 0; cb < C8; cb += 256) {   // 256 chunks (2048 channels) per pass; thread t: chunk cb + t % nch, voxel lane t / nch
+    const int nch = min(256, C8 - cb);
+    const int lanes = 256 / nch;            // voxel lanes per chunk (>= 1)
+    const int ch = threadIdx.x % nch, vl = threadIdx.x / nch;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (vl < lanes) {
+      for (int v = vl; v < nvox; v += lanes) {
+        const int dx = v % wx; const int t = v / wx; const int dy = t % wy; const int dz = t / wy;
+        const long long vox = (((long long)n * D + z0 + dz) * H + y0 + dy) * W + x0 + dx;
+        float f[8];
+        unpack8(ldg16_stream(x + vox * ldx + (cb + ch) * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += relu ? fmaxf(f[j], 0.f) : f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[threadIdx.x * 8 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < nch) {
+      float s[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+      for (int l = 0; l < lanes; ++l)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += part[(l * nch + threadIdx.x) * 8 + j];
+      const float inv = 1.f / (float)nvox;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (cb + threadIdx.x) * 8 + j;
+        out[(((long long)n * C + c) * OD + oz) * OH * OW + oy * OW + ox] = s[j] * inv;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -206,7 +263,28 @@ int b3d_pool_fwd(const void* x, long long ldx, const float* mask, void* out, lon
   B3D_REQUIRE(C % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "pool_fwd: need even dims and C%%8==0");
   const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
   pool_fwd_kernel<<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, mask, (bf16*)out, ldo, N,
-                                                                           D, H, W, C); ++g_b3d_launches;
+                                                                           D, H, W, C, 0); ++g_b3d_launches;
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// out = MaxPool3d(2)(ReLU(x))   (nn.ReLU + nn.MaxPool3d(2) of BrainTumorClassifier.features, main.py:307-312)
+int b3d_relu_pool_fwd(const void* x, long long ldx, void* out, long long ldo, int N, int D, int H, int W, int C, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "relu_pool_fwd: need even dims and C%%8==0");
+  const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
+  pool_fwd_kernel<<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, nullptr, (bf16*)out, ldo, N,
+                                                                           D, H, W, C, 1); ++g_b3d_launches;
+  B3D_CHECK_CUDA(cudaGetLastError());
+  return B3D_OK;
+}
+
+// out[n][c][oz][oy][ox] (fp32, the reference's NCDHW flatten order) = mean over the adaptive window of ReLU(x)
+// window of output index o along an axis of length L with O outputs: [floor(o*L/O), ceil((o+1)*L/O))   (ATen)
+int b3d_relu_adaptive_avgpool(const void* x, long long ldx, float* out, int N, int D, int H, int W, int C, int OD, int OH,
+                              int OW, int relu, void* stream) {
+  B3D_REQUIRE(C % 8 == 0 && OD > 0 && OH > 0 && OW > 0 && OD <= D && OH <= H && OW <= W, "adaptive_avgpool: bad shape");
+  dim3 grid(OD * OH * OW, N);
+  relu_adaptive_avgpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, D, H, W, C, OD, OH, OW, relu); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

@@ -49,3 +49,19 @@ def tumor_volumes(mask):
     cls, sl = ops.voxel_counts(mask)
     cls, sl = cls.cpu().tolist(), sl.cpu().tolist()
     return {"tumor_voxels": int(sum(cls[1:])), "class_voxels": cls, "slice_voxels": sl}
+
+
+CLASS_NAMES = ("Background", "Necrotic Core", "Peritumoral Edema", "Enhancing Tumor")   # main.py:417
+
+
+def classify(model, volume):
+    """classify_tumor call site (main.py:408-418): eval forward of BrainTumorClassifier, softmax, arg-max and its probability.
+    Returns (predicted class [N] int64, confidence [N] fp32, probabilities [N,K]) on the device — one D2H copy for the caller."""
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        prob = torch.softmax(model(volume), dim=1)
+    if was_training:
+        model.train()
+    conf, pred = prob.max(dim=1)
+    return pred, conf, prob

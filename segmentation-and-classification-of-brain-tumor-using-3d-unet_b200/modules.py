@@ -228,3 +228,41 @@ class UNet3D(nn.Module):
         if self.training and len(outs) > 1:
             return outs[0], list(outs[1:])
         return outs[0]
+
+
+class BrainTumorClassifier(nn.Module):
+    """CNN tumour-type classifier — main.py:301-328, used by `classify_tumor` (main.py:398-425) in eval mode under no_grad.
+
+    Same layers / state_dict keys as the reference (`features.{0,3,6}`, `classifier.{0,3}`).  The three 3x3x3 convolutions run
+    on the tcgen05 implicit-GEMM kernels, ReLU+MaxPool and ReLU+AdaptiveAvgPool on the bandwidth kernels of pool_layout.cu;
+    the two Linear layers (8192x512, 512xK: 8 MFLOP per sample) are plain library GEMMs.  Inference only: the reference never
+    trains this model, and train mode (Dropout(0.5) active) or a forward that needs gradients raises.  D, H, W must be
+    multiples of 4 (the two MaxPool3d(2) stages; nn.MaxPool3d would floor other sizes)."""
+
+    def __init__(self, num_classes=4):
+        super().__init__()
+        self.features = nn.Sequential(
+            nn.Conv3d(4, 32, 3, 1, 1), nn.ReLU(), nn.MaxPool3d(2),
+            nn.Conv3d(32, 64, 3, 1, 1), nn.ReLU(), nn.MaxPool3d(2),
+            nn.Conv3d(64, 128, 3, 1, 1), nn.ReLU(), nn.AdaptiveAvgPool3d((4, 4, 4)))
+        self.classifier = nn.Sequential(nn.Linear(128 * 4 * 4 * 4, 512), nn.ReLU(), nn.Dropout(0.5), nn.Linear(512, num_classes))
+
+    def forward(self, x):
+        _require_cuda(x, "BrainTumorClassifier")
+        if self.training:
+            raise NotImplementedError("b200 BrainTumorClassifier: inference only (call .eval(); the reference never trains it)")
+        n, cin, d, h, w = x.shape
+        if cin != 4:
+            raise ValueError("BrainTumorClassifier expects 4 input channels, got %d" % cin)
+        if d % 4 or h % 4 or w % 4 or min(d, h, w) < 16:
+            raise ValueError("BrainTumorClassifier (b200 path): D,H,W must be multiples of 4 and >= 16, got %s" % ((d, h, w),))
+        with torch.no_grad():
+            a = ops.to_ndhwc_bf16(x.detach(), 16)
+            for idx, last in ((0, False), (3, False), (6, True)):
+                conv = self.features[idx]
+                wp, _, rows = Fn.packed(conv.weight, ops.PACK_FPROP)
+                a, _ = ops.conv_fprop(a, wp, rows, conv.out_channels, 3, bias=conv.bias)
+                a = ops.relu_adaptive_avgpool(a, (4, 4, 4)) if last else ops.relu_pool_fwd(a)
+            fc1, fc2 = self.classifier[0], self.classifier[3]
+            hdn = torch.relu(torch.nn.functional.linear(a, fc1.weight, fc1.bias))
+            return torch.nn.functional.linear(hdn, fc2.weight, fc2.bias)

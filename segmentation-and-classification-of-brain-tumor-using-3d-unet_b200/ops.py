@@ -441,6 +441,25 @@ def pool_fwd(x, mask=None):
     return out
 
 
+def relu_pool_fwd(x):
+    """MaxPool3d(2)(ReLU(x)) — BrainTumorClassifier.features (main.py:307-312)."""
+    n, d, h, w, c = x.shape
+    out = new_act(n, d // 2, h // 2, w // 2, c, x.device)
+    check(_L().b3d_relu_pool_fwd(ptr(x), c_ll(ld(x)), ptr(out), c_ll(ld(out)), c_int(n), c_int(d), c_int(h), c_int(w), c_int(c),
+                                 stream_ptr()))
+    return out
+
+
+def relu_adaptive_avgpool(x, osize, relu=True):
+    """AdaptiveAvgPool3d(osize)(ReLU(x)) -> fp32 [N, C*od*oh*ow] in the reference's NCDHW flatten order (main.py:315,326)."""
+    n, d, h, w, c = x.shape
+    od, oh, ow = osize
+    out = torch.empty((n, c * od * oh * ow), dtype=torch.float32, device=x.device)
+    check(_L().b3d_relu_adaptive_avgpool(ptr(x), c_ll(ld(x)), ptr(out), c_int(n), c_int(d), c_int(h), c_int(w), c_int(c),
+                                         c_int(od), c_int(oh), c_int(ow), c_int(1 if relu else 0), stream_ptr()))
+    return out
+
+
 def pool_bwd(x, mask, dy, dx=None, accumulate=False):
     n, d, h, w, c = x.shape
     if dx is None:

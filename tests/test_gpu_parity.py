@@ -461,3 +461,30 @@ def test_single_channel_input_vs_oracle():
     assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss)
     assert model.downs[0].double_conv[0].weight.grad.shape == (16, 1, 3, 3, 3)
     _check_grads(model, rgrads, "cin1", _oracle_autocast_grads(sd, x, y, feats))
+
+
+@pytest.mark.parametrize("name,n,size,seed", [("a", 2, (32, 32, 32), 21), ("b", 1, (16, 32, 48), 22), ("c", 1, (64, 64, 64), 23)])
+def test_classifier_vs_reference_golden_and_oracle(name, n, size, seed):
+    """BrainTumorClassifier (main.py:301-328): eval forward against the reference's own outputs
+    (tests/golden/classifier.npz) and the oracle; bf16 convolutions -> 2.5e-2 relative on the logits, same predicted class
+    whenever the reference's top-2 margin exceeds that error."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "classifier.npz"))
+    sd = O.make_classifier_state_dict(4, seed=seed)
+    x, _ = O.make_inputs(n, *size, seed=seed)
+    model = U.BrainTumorClassifier(4)
+    assert [(k, tuple(v.shape)) for k, v in model.state_dict().items()] == O.classifier_param_shapes(4)
+    model.load_state_dict(sd)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        got = model(x.to(DEV)).cpu()
+    ref = torch.from_numpy(z["logits_" + name])
+    orc = O.classifier_forward(x, sd)
+    assert got.shape == ref.shape == orc.shape
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 2.5e-2 * scale, (got, ref)
+    assert float((got - orc).abs().max()) <= 2.5e-2 * scale
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 5e-2 * scale
+    assert torch.equal(got.argmax(1)[clear], ref.argmax(1)[clear])
+    with pytest.raises(NotImplementedError):
+        model.train()(x.to(DEV))

@@ -122,3 +122,22 @@ def test_voxel_counts_semantics():
     tumour, per_class, per_slice = O.voxel_counts(mask)
     assert tumour == sum(per_class[1:]) == sum(per_slice)
     assert sum(per_class) == mask.numel() and len(per_slice) == 7
+
+
+def test_classifier_oracle_matches_reference_golden():
+    """oracle.classifier_forward against the outputs of the reference's own BrainTumorClassifier (main.py:301-328), stored by
+    tests/golden/make_golden_classifier.py."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import unet3d_oracle as O
+    CASES = [("a", 2, (32, 32, 32), 21), ("b", 1, (16, 32, 48), 22), ("c", 1, (64, 64, 64), 23)]   # = make_golden_classifier.CASES
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "classifier.npz"))
+    assert [s.split(" ")[0] for s in z["keys"]] == [k for k, _ in O.classifier_param_shapes(4)]
+    for name, n, (d, h, w), seed in CASES:
+        sd = O.make_classifier_state_dict(4, seed=seed)
+        x, _ = O.make_inputs(n, d, h, w, seed=seed)
+        got = O.classifier_forward(x, sd)
+        ref = torch.from_numpy(z["logits_" + name])
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
