@@ -288,6 +288,7 @@ def main():
         for _ in range(2):   # the eager allocator pool is cold after the capture: warm it before timing the eager pass
             eager_step(xd, yd)
     ops.PROFILE = []
+    ops.PROFILE_BW = []
     l0 = lib.b3d_launch_count()
     barrier()
     e0.record()
@@ -298,6 +299,7 @@ def main():
     ms_prof = e0.elapsed_time(e1)
     launches = lib.b3d_launch_count() - l0
     prof, ops.PROFILE = ops.PROFILE, None
+    prof_bw, ops.PROFILE_BW = ops.PROFILE_BW, None
     ops.WGRAD_SIDE, ops.WGRAD_STREAM = side_saved
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -348,6 +350,18 @@ def main():
     for name, (fl, tms, cnt) in fam.items():
         fams[name] = {"tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None, "ms_per_step": tms / args.steps,
                       "launches_per_step": cnt / args.steps, "gflop_per_launch": fl / max(cnt, 1) / 1e9}
+    # bandwidth-bound families: compulsory bytes (every input once + every output once) / CUDA-event time
+    bw = {}
+    for name, nbytes, a, b, tag in prof_bw:
+        if name == "wgrad3_bytes":
+            continue
+        dd = bw.setdefault(name, [0.0, 0.0, 0])
+        dd[0] += nbytes; dd[1] += a.elapsed_time(b); dd[2] += 1
+    bw_fams = {}
+    for name, (nb, tms, cnt) in bw.items():
+        gbs = nb / (tms * 1e-3) / 1e9 if tms > 0 else None
+        bw_fams[name] = {"gbs": gbs, "frac_of_hbm_peak": (gbs / peaks["hbm_gbs"]) if gbs else None, "ms_per_step": tms / args.steps,
+                         "launches_per_step": cnt / args.steps, "compulsory_mb_per_step": nb / args.steps / 1e6}
     if "conv3" in fam:
         fl, tms, cnt = fam["conv3"]
         ach = fl / (tms * 1e-3) / 1e12
@@ -409,7 +423,7 @@ def main():
                        "global_batch": world * PER_GPU_BATCH, "parallelism": "dp%d" % world, "cuda_graph": graphed,
                        "l2": "no explicit flush: one step streams >5 GB of activations (>> 126 MB L2)"},
             "conv_tflops_whole_step": TRAIN_FLOP_PER_VOXEL * vox_per_step / world / (ms / args.steps * 1e-3) / 1e12,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams, "bandwidth_families": bw_fams,
             "inference": inference, "cpu_baseline": cpu_baseline,
         }
         real_stdout.write(json.dumps(line) + "\n")

@@ -20,6 +20,30 @@ EPS = 1e-5
 PROFILE = None  # bench.py sets this to a list: (family, algorithmic flops, start event, end event) per tensor-core call
 
 
+PROFILE_BW = None  # bench.py: list of (family, compulsory HBM bytes, start event, end event, tag) per bandwidth-bound call
+
+
+class _prof_bw:
+    """CUDA events around a bandwidth-bound call together with its COMPULSORY traffic (every input once + every output once,
+    SURVEY §8d) — bench.py turns them into achieved GB/s against the measured HBM peak."""
+
+    def __init__(self, family, nbytes, tag=""):
+        self.family, self.nbytes, self.tag = family, nbytes, tag
+
+    def __enter__(self):
+        if PROFILE_BW is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE_BW is not None:
+            self.b.record()
+            PROFILE_BW.append((self.family, self.nbytes, self.a, self.b, self.tag))
+        return False
+
+
 class _prof:
     def __init__(self, family, flops, tag=""):
         self.family, self.flops, self.tag = family, flops, tag
@@ -319,7 +343,8 @@ def _conv_wgrad(x, dy, cin_real, cout, ks, dw=None, accumulate=False):
     cout_pad = roundup(cout, 16)
     assert dy.shape[-1] == cout and (cout_pad == cout or ld(dy) >= cout_pad), "dy must expose padded channels"
     ws = torch.empty(ks ** 3 * cin * cout_pad, dtype=torch.float32, device=dev)
-    with _prof("wgrad", 2.0 * n * d * h * w * cin_real * cout * ks ** 3, "wgrad%d %dx%dx%dx%d %d,%d" % (ks, n, d, h, w, cin, cout)):
+    with _prof("wgrad", 2.0 * n * d * h * w * cin_real * cout * ks ** 3, "wgrad%d %dx%dx%dx%d %d,%d" % (ks, n, d, h, w, cin, cout)), \
+            _prof_bw("wgrad_pw" if ks == 1 else "wgrad3_bytes", n * d * h * w * (cin + cout) * 2, "wgrad%d" % ks):
         check(_L().b3d_conv_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
                                   c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cin_real), c_int(cout), c_int(ks), ptr(ws),
                                   c_sz(ws.numel() * 4), ptr(_lib.err_flag(dev)), stream_ptr()))
@@ -362,10 +387,12 @@ def gn_apply(y, stats, gamma, beta, groups, relu, res=None, res_stats=None, res_
     if out is None:
         out = torch.empty_like(y, memory_format=torch.contiguous_format)
     res_mode = 0 if res is None else (1 if res_stats is not None else 2)
-    check(_L().b3d_gn_apply(ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta), c_int(groups), c_int(1 if relu else 0),
-                            c_int(res_mode), ptr(res), c_ll(ld(res) if res is not None else 0), ptr(res_stats),
-                            ptr(res_gamma), ptr(res_beta), c_int(res_groups if res_groups else 1), ptr(out), c_ll(ld(out)),
-                            c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
+    tb = n * v * c * 2
+    with _prof_bw("gn_fwd", tb * (2 if res is None else 3), "gn_apply C%d V%d" % (c, v)):
+        check(_L().b3d_gn_apply(ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta), c_int(groups), c_int(1 if relu else 0),
+                                c_int(res_mode), ptr(res), c_ll(ld(res) if res is not None else 0), ptr(res_stats),
+                                ptr(res_gamma), ptr(res_beta), c_int(res_groups if res_groups else 1), ptr(out), c_ll(ld(out)),
+                                c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
     return out
 
 
@@ -374,17 +401,18 @@ def gn_bwd(dy, y, stats, gamma, beta, groups, relu, dx=None, accumulate=False, s
     reduction phase is skipped (a producer already computed it)."""
     n, v, c = _nvc(y)
     dev = y.device
-    if sums is None:
-        sums = zeros_scratch((n, c, 2), torch.float64, dev)
-        check(_L().b3d_gn_bwd_reduce(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta),
-                                     c_int(groups), c_int(1 if relu else 0), ptr(sums), c_int(n), c_ll(v), c_int(c),
-                                     c_float(EPS), stream_ptr()))
-    if dx is None:
-        dx = torch.empty_like(y, memory_format=torch.contiguous_format)
-        accumulate = False
-    check(_L().b3d_gn_bwd_apply(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta), c_int(groups),
-                                c_int(1 if relu else 0), ptr(sums), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
-                                c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
+    with _prof_bw("gn_bwd", n * v * c * 2 * (5 if sums is None else 3), "gn_bwd C%d V%d" % (c, v)):
+        if sums is None:
+            sums = zeros_scratch((n, c, 2), torch.float64, dev)
+            check(_L().b3d_gn_bwd_reduce(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta),
+                                         c_int(groups), c_int(1 if relu else 0), ptr(sums), c_int(n), c_ll(v), c_int(c),
+                                         c_float(EPS), stream_ptr()))
+        if dx is None:
+            dx = torch.empty_like(y, memory_format=torch.contiguous_format)
+            accumulate = False
+        check(_L().b3d_gn_bwd_apply(ptr(dy), c_ll(ld(dy)), ptr(y), c_ll(ld(y)), ptr(stats), ptr(gamma), ptr(beta), c_int(groups),
+                                    c_int(1 if relu else 0), ptr(sums), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
+                                    c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr()))
     dgamma = dbeta = None
     if want_param_grads:
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
@@ -409,9 +437,8 @@ def gn_bwd_dual(dy, ya, stats_a, gamma_a, beta_a, yb, stats_b, gamma_b, groups):
     sums_b = zeros_scratch((n, c, 2), torch.float64, dev)
     dxa = torch.empty_like(ya, memory_format=torch.contiguous_format)
     dxb = torch.empty_like(yb, memory_format=torch.contiguous_format)
-    rc = _L().b3d_gn_bwd_dual(ptr(dy), c_ll(ld(dy)), ptr(ya), c_ll(ld(ya)), ptr(stats_a), ptr(gamma_a), ptr(beta_a), ptr(yb),
-                              c_ll(ld(yb)), ptr(stats_b), ptr(gamma_b), c_int(groups), ptr(sums_a), ptr(sums_b), ptr(dxa),
-                              c_ll(ld(dxa)), ptr(dxb), c_ll(ld(dxb)), c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr())
+    with _prof_bw("gn_bwd", n * v * c * 2 * 8, "gn_bwd_dual C%d V%d" % (c, v)):
+        rc = _dual_call(dy, ya, stats_a, gamma_a, beta_a, yb, stats_b, gamma_b, groups, sums_a, sums_b, dxa, dxb, n, v, c)
     if rc == 1:
         return None
     check(rc)
@@ -419,6 +446,12 @@ def gn_bwd_dual(dy, ya, stats_a, gamma_a, beta_a, yb, stats_b, gamma_b, groups):
     check(_L().b3d_gn_param_grad(ptr(sums_a), c_int(n), c_int(c), ptr(g[0]), ptr(g[1]), c_int(0), stream_ptr()))
     check(_L().b3d_gn_param_grad(ptr(sums_b), c_int(n), c_int(c), ptr(g[2]), ptr(g[3]), c_int(0), stream_ptr()))
     return dxa, g[0], g[1], dxb, g[2], g[3]
+
+
+def _dual_call(dy, ya, stats_a, gamma_a, beta_a, yb, stats_b, gamma_b, groups, sums_a, sums_b, dxa, dxb, n, v, c):
+    return _L().b3d_gn_bwd_dual(ptr(dy), c_ll(ld(dy)), ptr(ya), c_ll(ld(ya)), ptr(stats_a), ptr(gamma_a), ptr(beta_a), ptr(yb),
+                              c_ll(ld(yb)), ptr(stats_b), ptr(gamma_b), c_int(groups), ptr(sums_a), ptr(sums_b), ptr(dxa),
+                              c_ll(ld(dxa)), ptr(dxb), c_ll(ld(dxb)), c_int(n), c_ll(v), c_int(c), c_float(EPS), stream_ptr())
 
 
 def add_bf16(a, b, out=None):
