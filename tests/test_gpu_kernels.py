@@ -425,3 +425,29 @@ def test_groupnorm_dual_backward(c, s):
     sxb, sgb, sbb = ops.gn_bwd(dout, yb, stb, gb, bb, groups, False)
     _close_bf16(dxa, sxa.float(), tol=1.0 / 64)
     _close_bf16(dxb, sxb.float(), tol=1.0 / 64)
+
+
+@pytest.mark.parametrize("dims,cin,cout,alias", [
+    ((1, 64, 32, 32), 16, 32, True),    # in-place dx += conv(dy) (attention-gate dgrad shape)
+    ((1, 64, 32, 32), 32, 64, False),   # separate addend, output into a channel slice of a wider buffer
+    ((2, 32, 32, 33), 32, 16, True),    # ragged voxel count
+    ((1, 8, 16, 16), 16, 32, True),     # small volume
+    ((1, 32, 64, 32), 64, 32, False),   # wider K
+])
+def test_conv1_fused_addend(dims, cin, cout, alias):
+    """out = add + conv1x1(x): the branch-gradient accumulation of the backward pass (`dx += ...`)."""
+    n, d, h, w = dims
+    x = _bf(n, d, h, w, cin, seed=61)
+    wt = (_bf(cout, cin, 1, 1, 1, seed=62).float() / cin ** 0.5).to(BF).float()
+    wp, kp, rows = ops.pack_weight(wt, ops.PACK_FPROP)
+    add = _bf(n, d, h, w, cout, seed=63)
+    ref = _ndhwc(F.conv3d(_ncdhw(x), wt)) + add.float()
+    if alias:
+        out = add.clone()
+        ops.conv_fprop(x, wp, rows, cout, 1, out=out, add=out)
+    else:
+        wide = torch.zeros(n, d, h, w, 2 * cout, dtype=BF, device=DEV)
+        out = wide[..., cout:]
+        ops.conv_fprop(x, wp, rows, cout, 1, out=out, add=add)
+        assert float(wide[..., :cout].abs().max()) == 0.0
+    _close_bf16(out, ref)
