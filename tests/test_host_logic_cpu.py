@@ -54,3 +54,44 @@ def test_packed_weight_cache_lives_on_the_parameter(monkeypatch):
     q = torch.nn.Parameter(p.detach().clone())   # another parameter never sees p's cache
     functional.packed(q, 0)
     assert len(calls) == 5 and "_b3d_pack" in q.__dict__ and q.__dict__["_b3d_pack"] is not p.__dict__["_b3d_pack"]
+
+
+def test_optimizer_step_invalidates_the_pack_cache(monkeypatch):
+    """torch's fused AdamW updates parameters WITHOUT bumping their version counters (checked here), so the packed-weight
+    cache is also invalidated by a global optimizer post-step hook — for every torch optimizer, fused or not."""
+    calls = []
+
+    def fake_pack(w, mode):
+        calls.append(mode)
+        return torch.zeros(1), 16, 16
+    monkeypatch.setattr(ops, "pack_weight", fake_pack)
+    for kwargs in ({"fused": True}, {"foreach": True}, {}):
+        p = torch.nn.Parameter(torch.randn(4, 4, 3, 3, 3))
+        opt = torch.optim.AdamW([p], lr=1e-3, **kwargs)
+        calls.clear()
+        functional.packed(p, 0); functional.packed(p, 0)
+        assert len(calls) == 1
+        p.grad = torch.randn_like(p)
+        before = p.detach().clone()
+        opt.step()
+        assert not torch.equal(before, p.detach())
+        functional.packed(p, 0)
+        assert len(calls) == 2, "packed weights survived an optimizer step (%s)" % (kwargs,)
+    sgd_p = torch.nn.Parameter(torch.randn(4, 4, 1, 1, 1))
+    sgd = torch.optim.SGD([sgd_p], lr=0.1)
+    calls.clear()
+    functional.packed(sgd_p, 0)
+    sgd_p.grad = torch.ones_like(sgd_p)
+    sgd.step()
+    functional.packed(sgd_p, 0)
+    assert len(calls) == 2
+
+
+def test_zeros_scratch_and_side_branch_are_inert_on_cpu():
+    """ops.zeros_scratch falls back to torch.zeros off-GPU; ops.side_branch(False, ...) is a no-op context."""
+    z = ops.zeros_scratch((2, 3, 2), torch.float64, torch.device("cpu"))
+    assert z.shape == (2, 3, 2) and z.dtype == torch.float64 and float(z.abs().sum()) == 0.0
+    with ops.side_branch(False, z) as br:
+        z += 1
+    br.join()
+    assert float(z.sum()) == 12.0
