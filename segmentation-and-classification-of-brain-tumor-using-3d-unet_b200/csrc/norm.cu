@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
 //   x̂ = x*ka + kb ;  relu test: x*S + T <= 0 ;  dx = dz*P - Q - x*R   with P = γ*rstd, R = ka*Cg, Q = Bg + kb*Cg
 //   (Bg, Cg = rstd * mean_g(γ·Σdz), rstd * mean_g(γ·Σdz·x̂): the group terms of the standard formula).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_dual_reduce_kernel(
+template <int OCC>
+__global__ void __launch_bounds__(GN_THREADS, OCC) gn_bwd_dual_reduce_kernel(
     const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ ya, long long ldya, const double* __restrict__ stats_a,
     const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const bf16* __restrict__ yb, long long ldyb,
     const double* __restrict__ stats_b, int G, double* __restrict__ sums_a, double* __restrict__ sums_b, long long V, int C,
@@ -380,7 +381,8 @@ __global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_dual_reduce_kernel(
   }
 }
 
-__global__ void __launch_bounds__(GN_THREADS, 2) gn_bwd_dual_apply_kernel(
+template <int OCC>
+__global__ void __launch_bounds__(GN_THREADS, OCC) gn_bwd_dual_apply_kernel(
     const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ ya, long long ldya, const double* __restrict__ stats_a,
     const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const double* __restrict__ sums_a,
     const bf16* __restrict__ yb, long long ldyb, const double* __restrict__ stats_b, const float* __restrict__ gamma_b,
@@ -566,13 +568,24 @@ int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ld
   if (C > 512 || (GN_THREADS % C8) != 0) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   const int per_sample = std::max(1, std::min(ew_blocks(V * C8, GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
-  gn_bwd_dual_reduce_kernel<<<dim3(per_sample, N), GN_THREADS, (6 * (size_t)C) * sizeof(float) + 4 * (size_t)C * sizeof(double), st>>>(
-      (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, (const bf16*)yb, ldyb, stats_b, G, sums_a, sums_b,
-      V, C, eps); ++g_b3d_launches;
+  // OCC = resident blocks per SM the register allocation is capped for: 2 (121/126 registers, no spills; ncu: 25 % warps
+  // active, 4.3-4.6 TB/s, profiles/ncu_r1_gn_bwd_dual.txt) or 3 (80 registers, ~150 bytes of spills).  Measured at
+  // 2x128^3x32 (scripts/gn_dual_once.py): OCC 2 0.485 ms, OCC 3 0.635 ms — the spills cost more than the extra warps hide,
+  // so 2 is the default; B3D_GN_DUAL_OCC=3 keeps the experiment reproducible.
+  static const int occ = getenv("B3D_GN_DUAL_OCC") ? atoi(getenv("B3D_GN_DUAL_OCC")) : 2;
+  const size_t smem_r = (6 * (size_t)C) * sizeof(float) + 4 * (size_t)C * sizeof(double), smem_a = 8 * (size_t)C * sizeof(float);
+  const dim3 grid_r(per_sample, N), grid_a(ew_blocks(V * C8, GN_THREADS * 2), N);
+#define DUAL_ARGS_R (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, (const bf16*)yb, ldyb, stats_b, G, sums_a, sums_b, V, C, eps
+#define DUAL_ARGS_A (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, sums_a, (const bf16*)yb, ldyb, stats_b, gamma_b, sums_b, G, (bf16*)dxa, lddxa, (bf16*)dxb, lddxb, V, C, eps
+  if (occ == 3) gn_bwd_dual_reduce_kernel<3><<<grid_r, GN_THREADS, smem_r, st>>>(DUAL_ARGS_R);
+  else gn_bwd_dual_reduce_kernel<2><<<grid_r, GN_THREADS, smem_r, st>>>(DUAL_ARGS_R);
+  ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
-  gn_bwd_dual_apply_kernel<<<dim3(ew_blocks(V * C8, GN_THREADS * 2), N), GN_THREADS, 8 * (size_t)C * sizeof(float), st>>>(
-      (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, sums_a, (const bf16*)yb, ldyb, stats_b, gamma_b,
-      sums_b, G, (bf16*)dxa, lddxa, (bf16*)dxb, lddxb, V, C, eps); ++g_b3d_launches;
+  if (occ == 3) gn_bwd_dual_apply_kernel<3><<<grid_a, GN_THREADS, smem_a, st>>>(DUAL_ARGS_A);
+  else gn_bwd_dual_apply_kernel<2><<<grid_a, GN_THREADS, smem_a, st>>>(DUAL_ARGS_A);
+  ++g_b3d_launches;
+#undef DUAL_ARGS_R
+#undef DUAL_ARGS_A
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
