@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md §Measurement).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (under torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the same path
+    python bench.py --gpus N --steps K --warmup W                    # our arm (under torchrun for N > 1), cfg 3, weak scaling
+    python bench.py --scaling strong --gpus N ...                    # cfg 4: fixed GLOBAL batch 16 (16/N volumes per GPU)
+    python bench.py --config cfg5 --gpus N ...                       # cfg 5: wide model [64..1024], 1 x 4 x 160x192x160 per GPU
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU implementation of the same path
 
-Workload (BASELINE.json configs[2], "cfg 3"): one training step = forward + deep-supervised Dice/focal/boundary loss +
+Default workload (BASELINE.json configs[2], "cfg 3"): one training step = forward + deep-supervised Dice/focal/boundary loss +
 backward (+ gradient all-reduce for N > 1) + AdamW step of the default-architecture enhanced 3D U-Net on a synthetic
-batch of 2 volumes per GPU, 4 x 128^3, bf16 compute / fp32 parameters.  value = N * 2 * 128^3 * K / time  [voxels/s].
+batch of 2 volumes per GPU, 4 x 128^3, bf16 compute / fp32 parameters.  value = voxels of all ranks * K / time  [voxels/s].
 Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -23,11 +25,37 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "3D U-Net train voxels/s (4ch 128^3) at 1/2/4/8 B200; inference volumes/s"
-FEATURES = [32, 64, 128, 256, 512]
-PER_GPU_BATCH = 2
-SIZE = 128
-TRAIN_FLOP_PER_VOXEL = 1532476.0   # conv FLOPs fprop+dgrad+wgrad per input voxel, default arch
-FWD_FLOP_PER_VOXEL = 513215.0
+# conv FLOPs per input voxel (fprop / fprop+dgrad+wgrad), BASELINE.md §3 — analytic = hook-counted on the reference
+CONFIGS = {
+    "cfg3": {"features": [32, 64, 128, 256, 512], "per_gpu_batch": 2, "size": (128, 128, 128), "fwd_flop": 513215.0,
+             "train_flop": 1532476.0,
+             "workload": "cfg3: train step, batch 2/GPU, 4x128^3, default arch [32,64,128,256,512], dropout 0.2, "
+                         "DeepSupervisionLoss3D(CombinedLoss3D), step = fwd+loss+bwd(+NCCL grad all-reduce)+AdamW"},
+    "cfg4": {"features": [32, 64, 128, 256, 512], "global_batch": 16, "size": (128, 128, 128), "fwd_flop": 513215.0,
+             "train_flop": 1532476.0,
+             "workload": "cfg4: train step, GLOBAL batch 16 (16/N per GPU), 4x128^3, default arch [32,64,128,256,512], dropout "
+                         "0.2, DeepSupervisionLoss3D(CombinedLoss3D), step = fwd+loss+bwd(+NCCL grad all-reduce)+AdamW"},
+    "cfg5": {"features": [64, 128, 256, 512, 1024], "per_gpu_batch": 1, "size": (160, 192, 160), "fwd_flop": 2037501.0,
+             "train_flop": 6098168.0,
+             "workload": "cfg5: train step, batch 1/GPU, 4x160x192x160, wide arch [64,128,256,512,1024] (config.py:139), dropout "
+                         "0.2, DeepSupervisionLoss3D(CombinedLoss3D), step = fwd+loss+bwd(+NCCL grad all-reduce)+AdamW"},
+}
+L2_NOTE = "no explicit flush: one step streams >5 GB of activations (>> 126 MB L2)"
+
+
+def resolve_config(args, world):
+    """-> (name, cfg dict with per_gpu_batch resolved, `config` object of the JSON line — identical for both arms)."""
+    name = args.config
+    if args.scaling == "strong":
+        name = "cfg4"
+    cfg = dict(CONFIGS[name])
+    if "global_batch" in cfg:
+        if cfg["global_batch"] % world:
+            raise SystemExit("global batch %d does not divide over %d GPUs" % (cfg["global_batch"], world))
+        cfg["per_gpu_batch"] = cfg["global_batch"] // world
+    line_cfg = {"workload": cfg["workload"], "global_batch": world * cfg["per_gpu_batch"], "parallelism": "dp%d" % world,
+                "l2": L2_NOTE}
+    return name, cfg, line_cfg
 
 
 def _peaks():
@@ -40,6 +68,16 @@ def _peaks():
     except Exception:
         pass
     return p
+
+
+def _ncu_traffic():
+    """Per-kernel DRAM traffic of THIS build's dominant kernels: profiles/ncu_traffic.json, regenerated from an
+    `ncu --set full` capture by scripts/ncu_traffic.py (dram__bytes_read.sum + dram__bytes_write.sum per launch)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -116,19 +154,32 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+
 # ------------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the reference's own PyTorch CPU path (sliced classes when /root/reference is mounted,
-# else the pinned oracle restatement — the only places outside tests/ allowed to execute oracle/)
+# reference arm / CPU baseline: the reference's OWN PyTorch classes on the host cores — sliced live from /root/reference in
+# the build container, or from oracle/_ref/ (materialised by oracle/make_ref.py, shipped with the snapshot) on the GPU box;
+# the pinned oracle restatement ("port") only if neither exists.  The only places outside tests/ allowed to execute oracle/.
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_train_steps(steps, warmup, size=64, batch=1):
+def cpu_train_steps(cfg, steps, warmup):
+    """Times `steps` training steps of the reference implementation on a BOUNDED sample of the configured workload: ONE
+    volume of the per-GPU batch at the configured resolution for the default architecture (1 x 4 x 128^3 = the reference's
+    own 128^3 CPU probe of BASELINE.md §2), a 64^3 crop for the wide model.  Throughput is per voxel, so the sample rate is
+    directly comparable with the GPU arm's voxels/s."""
     from oracle import ref_slice
     from oracle import unet3d_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    x, y = O.make_inputs(batch, size, size, size, seed=0)
+    feats = list(cfg["features"])
+    size = tuple(cfg["size"]) if feats[0] <= 32 else (64, 64, 64)
+    if os.environ.get("B3D_CPU_SAMPLE_SIZE"):
+        size = (int(os.environ["B3D_CPU_SAMPLE_SIZE"]),) * 3
+    batch = 1
+    x, y = O.make_inputs(batch, size[0], size[1], size[2], seed=0)
     if ref_slice.available():
         ns = ref_slice.load()
         torch.manual_seed(0)
-        model = ns["UNet3D"](4, 4, features=list(FEATURES))
+        model = ns["UNet3D"](4, 4, features=feats)
+        model.train()
         crit = ns["DeepSupervisionLoss3D"]()
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
         kind = "reference"
@@ -138,43 +189,49 @@ def cpu_train_steps(steps, warmup, size=64, batch=1):
             loss = crit(model(x), y)
             loss.backward()
             opt.step()
-            return float(loss)
+            return float(loss.detach())
     else:
-        sd = O.make_state_dict(4, 4, FEATURES, seed=0)
+        sd = O.make_state_dict(4, 4, feats, seed=0)
         params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
         sd.update(params)
-        masks = O.make_dropout_masks(batch, FEATURES, 0.2)
+        masks = O.make_dropout_masks(batch, feats, 0.2)
         opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=1e-4)
         kind = "port"
 
         def step():
             opt.zero_grad()
-            main, deep, _ = O.unet_forward(x, sd, FEATURES, training=True, dropout_masks=masks)
+            main, deep, _ = O.unet_forward(x, sd, feats, training=True, dropout_masks=masks)
             loss = O.deep_supervision_loss(main, deep, y)
             loss.backward()
             opt.step()
-            return float(loss)
+            return float(loss.detach())
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    vox = batch * size ** 3
+    vox = batch * size[0] * size[1] * size[2]
+    full = tuple(cfg["size"])
+    what = "one volume of the per-GPU batch at full resolution" if size == full else "a %dx%dx%d crop of one volume" % size
     return {"value": vox / dt, "unit": "voxels/s", "cores": torch.get_num_threads(), "kind": kind,
-            "sample": "%d x 4 x %d^3 crop of the 2x4x128^3 step (fwd+DS loss+bwd+AdamW, fp32, %d timed steps after %d warm-up)"
-                      % (batch, size, steps, warmup), "ms_per_step": dt * 1e3}
+            "sample": "%s (%d x 4 x %dx%dx%d), same step: fwd + DS loss + bwd + AdamW, fp32, %s classes on the host CPU, "
+                      "%d timed steps after %d warm-up" % (what, batch, size[0], size[1], size[2],
+                                                           "the reference's own" if kind == "reference" else "oracle-port",
+                                                           steps, warmup),
+            "ms_per_step": dt * 1e3}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_train_steps(args.steps, args.warmup)
+    world = max(args.gpus, 1)
+    name, cfg, line_cfg = resolve_config(args, world)
+    cb = cpu_train_steps(cfg, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "voxels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3 train step (default arch, DS loss, AdamW), CPU sample: " + cb["sample"]},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": line_cfg,
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -188,14 +245,18 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-families", action="store_true", help="skip the eager per-kernel-family pass")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
     args.warmup = max(args.warmup, 3)
 
+    import ctypes
     import torch.distributed as dist
     import b3d  # noqa: F401
     import unet3d_b200 as U
@@ -205,6 +266,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_name, cfg, line_cfg = resolve_config(args, world)
+    feats, nb, (sd_, sh_, sw_) = list(cfg["features"]), cfg["per_gpu_batch"], cfg["size"]
+    vol = sd_ * sh_ * sw_
     # exactly ONE line on stdout: everything else that writes to fd 1 (NCCL prints a version banner there) goes to stderr
     sys.stdout.flush()
     real_stdout = os.fdopen(os.dup(1), "w")
@@ -215,19 +279,19 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
-    lib.b3d_launch_count.restype = __import__("ctypes").c_longlong
+    lib.b3d_launch_count.restype = ctypes.c_longlong
 
     torch.manual_seed(0)
-    model = U.UNet3D(4, 4, features=list(FEATURES), dropout_rate=0.2).to(dev)
+    model = U.UNet3D(4, 4, features=feats, dropout_rate=0.2).to(dev)
     model.train()
     crit = U.DeepSupervisionLoss3D()
     net = DataParallel(model) if world > 1 else model
     use_graph = not os.environ.get("B3D_NO_GRAPH")
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
+    opt = U.make_adamw(model, lr=1e-4, weight_decay=1e-4, capturable=use_graph)
 
     g = torch.Generator().manual_seed(1000 + rank)
-    x_host = torch.randn(PER_GPU_BATCH, 4, SIZE, SIZE, SIZE, generator=g).pin_memory()
-    y_host = torch.randint(0, 4, (PER_GPU_BATCH, SIZE, SIZE, SIZE), generator=g).pin_memory()
+    x_host = torch.randn(nb, 4, sd_, sh_, sw_, generator=g).pin_memory()
+    y_host = torch.randint(0, 4, (nb, sd_, sh_, sw_), generator=g).pin_memory()
     xd, yd = x_host.to(dev), y_host.to(dev)
 
     def eager_step(xi, yi):
@@ -258,6 +322,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         step(xd, yd)
     barrier()
@@ -276,36 +346,9 @@ def main():
         step(xd, yd)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.summary() if sampler else None
-    # per-kernel-family CUDA events + launch count: an eager pass of the SAME step right after the timed region (a replayed
-    # CUDA graph has no host-side hooks between its kernels); it is not part of `value`
-    # in this pass every kernel runs alone on one stream (the weight-gradient side stream is off), so the CUDA events
-    # around a launch measure that kernel, not the kernels it overlaps with in the real step
-    side_saved = (ops.WGRAD_SIDE, ops.WGRAD_STREAM)
-    ops.WGRAD_SIDE, ops.WGRAD_STREAM = False, None
-    if graphed:
-        for _ in range(2):   # the eager allocator pool is cold after the capture: warm it before timing the eager pass
-            eager_step(xd, yd)
-    ops.PROFILE = []
-    ops.PROFILE_BW = []
-    l0 = lib.b3d_launch_count()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        eager_step(xd, yd)
-    e1.record()
-    barrier()
-    ms_prof = e0.elapsed_time(e1)
-    launches = lib.b3d_launch_count() - l0
-    prof, ops.PROFILE = ops.PROFILE, None
-    prof_bw, ops.PROFILE_BW = ops.PROFILE_BW, None
-    ops.WGRAD_SIDE, ops.WGRAD_STREAM = side_saved
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    vox_per_step = world * PER_GPU_BATCH * SIZE ** 3
+    vox_per_step = world * nb * vol
     value = vox_per_step * args.steps / (ms * 1e-3)
 
     # ---- end to end: pinned host inputs, H2D inside the timed region, D2H of the loss ---------------------------------
@@ -326,58 +369,82 @@ def main():
             last = step(xi, yi).item()
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e = {"value": vox_per_step * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
            "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
            "ms_per_step": ms_e2e / args.steps, "last_loss": last}
 
-    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM), from CUDA events inside the timed region ----
+    # ---- per-kernel-family CUDA events + launch count: an eager pass of the SAME step after the timed regions (a replayed
+    # CUDA graph has no host-side hooks between its kernels); it is not part of `value`.  Every kernel runs alone on one
+    # stream here (the weight-gradient side stream is off), so the events around a launch measure that kernel only.
     peaks = _peaks()
-    fam = {}
-    for name, flops, a, b, tag in prof:
-        # families by kernel: conv3 = 3x3x3 fprop/dgrad (conv_zs.cu at levels 0-1, conv_igemm.cu below), pointwise = 1x1x1
-        # convs + ConvTranspose (conv_igemm.cu), wgrad3 = 3x3x3 weight gradients (conv_wg2.cu / conv_wgrad.cu), wgrad_pw
-        kind = tag.split(" ")[0] if tag else name
-        name = {"conv3": "conv3", "conv1": "pointwise", "convT": "pointwise", "convT_dgrad": "pointwise",
-                "wgrad3": "wgrad3", "wgrad1": "wgrad_pw", "wgradT": "wgrad_pw"}.get(kind, name)
-        d = fam.setdefault(name, [0.0, 0.0, 0])
-        d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
-    roof, fams = None, {}
-    for name, (fl, tms, cnt) in fam.items():
-        fams[name] = {"tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None, "ms_per_step": tms / args.steps,
-                      "launches_per_step": cnt / args.steps, "gflop_per_launch": fl / max(cnt, 1) / 1e9}
-    # bandwidth-bound families: compulsory bytes (every input once + every output once) / CUDA-event time
-    bw = {}
-    for name, nbytes, a, b, tag in prof_bw:
-        if name == "wgrad3_bytes":
-            continue
-        dd = bw.setdefault(name, [0.0, 0.0, 0])
-        dd[0] += nbytes; dd[1] += a.elapsed_time(b); dd[2] += 1
-    bw_fams = {}
-    for name, (nb, tms, cnt) in bw.items():
-        gbs = nb / (tms * 1e-3) / 1e9 if tms > 0 else None
-        bw_fams[name] = {"gbs": gbs, "frac_of_hbm_peak": (gbs / peaks["hbm_gbs"]) if gbs else None, "ms_per_step": tms / args.steps,
-                         "launches_per_step": cnt / args.steps, "compulsory_mb_per_step": nb / args.steps / 1e6}
-    if "conv3" in fam:
-        fl, tms, cnt = fam["conv3"]
-        ach = fl / (tms * 1e-3) / 1e12
-        roof = {"kernel": "zs_kernel / igemm_kernel (3x3x3 conv fprop + dgrad, tcgen05 implicit GEMM)", "bound": "tensor",
-                "achieved": ach,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
-                # dram__bytes_read+write of the representative launch (zs_kernel<32,32>, 32->32 @2x128^3, ncu --set full,
-                # profiles/ncu_r1_zs_32_32_final.txt) vs 536.9 MB algorithmic (one read + one write of a 268 MB tensor)
-                "traffic": 674.1e6, "traffic_kernel": "zs_kernel<32,32> 32->32 3x3x3 @2x128^3: 674 MB DRAM vs 537 MB algorithmic",
-                "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
-                "avg_launch_ms": tms / max(cnt, 1), "algorithmic_gflop_per_launch": fl / max(cnt, 1) / 1e9,
-                "share_of_step": tms / ms_prof,
-                "measured_in": "eager single-stream pass of the same step inside bench.py (CUDA events around every launch), %.2f ms/step"
-                               % (ms_prof / args.steps)}
+    roof, fams, bw_fams, launches, ms_prof = None, {}, {}, 0, None
+    if not args.no_families:
+        side_saved = (ops.WGRAD_SIDE, ops.WGRAD_STREAM)
+        ops.WGRAD_SIDE, ops.WGRAD_STREAM = False, None
+        if graphed:
+            for _ in range(2):   # the eager allocator pool is cold after the capture: warm it before timing the eager pass
+                eager_step(xd, yd)
+        ops.PROFILE = []
+        ops.PROFILE_BW = []
+        l0 = lib.b3d_launch_count()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            eager_step(xd, yd)
+        e1.record()
+        barrier()
+        ms_prof = e0.elapsed_time(e1)
+        launches = lib.b3d_launch_count() - l0
+        prof, ops.PROFILE = ops.PROFILE, None
+        prof_bw, ops.PROFILE_BW = ops.PROFILE_BW, None
+        ops.WGRAD_SIDE, ops.WGRAD_STREAM = side_saved
+        fam = {}
+        for name, flops, a, b, tag in prof:
+            # families by kernel: conv3 = 3x3x3 fprop/dgrad (conv_zs.cu at levels 0-1, conv_igemm.cu below), pointwise = 1x1x1
+            # convs + ConvTranspose, wgrad3 = 3x3x3 weight gradients (conv_wg2.cu / conv_wgrad.cu), wgrad_pw
+            kind = tag.split(" ")[0] if tag else name
+            name = {"conv3": "conv3", "conv1": "pointwise", "convT": "pointwise", "convT_dgrad": "pointwise",
+                    "wgrad3": "wgrad3", "wgrad1": "wgrad_pw", "wgradT": "wgrad_pw"}.get(kind, name)
+            d = fam.setdefault(name, [0.0, 0.0, 0])
+            d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+        for name, (fl, tms, cnt) in fam.items():
+            fams[name] = {"tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None, "ms_per_step": tms / args.steps,
+                          "launches_per_step": cnt / args.steps, "gflop_per_launch": fl / max(cnt, 1) / 1e9}
+        # bandwidth-bound families: compulsory bytes (every input once + every output once) / CUDA-event time
+        bw = {}
+        for name, nbytes, a, b, tag in prof_bw:
+            if name == "wgrad3_bytes":
+                continue
+            dd = bw.setdefault(name, [0.0, 0.0, 0])
+            dd[0] += nbytes; dd[1] += a.elapsed_time(b); dd[2] += 1
+        for name, (nb_, tms, cnt) in bw.items():
+            gbs = nb_ / (tms * 1e-3) / 1e9 if tms > 0 else None
+            bw_fams[name] = {"gbs": gbs, "frac_of_hbm_peak": (gbs / peaks["hbm_gbs"]) if gbs else None,
+                             "ms_per_step": tms / args.steps, "launches_per_step": cnt / args.steps,
+                             "compulsory_mb_per_step": nb_ / args.steps / 1e6}
+        if "conv3" in fam:
+            fl, tms, cnt = fam["conv3"]
+            ach = fl / (tms * 1e-3) / 1e12
+            tr = _ncu_traffic() or {}
+            rep = (tr.get("kernels") or {}).get(tr.get("roofline_kernel", ""), None)
+            roof = {"kernel": "zs_kernel / igemm_kernel (3x3x3 conv fprop + dgrad, tcgen05 implicit GEMM)", "bound": "tensor",
+                    "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"],
+                    # dram__bytes_read+write per launch of the family's largest launch, from the committed ncu capture of this
+                    # kernel set (profiles/ncu_traffic.json <- scripts/ncu_traffic.py); null when no capture is committed
+                    "traffic": rep["dram_bytes"] if rep else None,
+                    "traffic_kernel": ("%s: %.1f MB DRAM vs %.1f MB algorithmic (%s)" % (
+                        tr["roofline_kernel"], rep["dram_bytes"] / 1e6, rep["algorithmic_bytes"] / 1e6, tr.get("source", "")))
+                    if rep else None,
+                    "peak_source": peaks["src"] + " (sustained bf16, kernel timed inside a long step)",
+                    "avg_launch_ms": tms / max(cnt, 1), "algorithmic_gflop_per_launch": fl / max(cnt, 1) / 1e9,
+                    "flops": "2*voxels*Cin*Cout*27 with the REAL Cin/Cout of every launch (zero-padded channels not counted)",
+                    "share_of_step": tms / ms_prof,
+                    "measured_in": "eager single-stream pass of the same step inside bench.py (CUDA events around every "
+                                   "launch), %.2f ms/step" % (ms_prof / args.steps)}
 
-    # ---- inference (cfg 2): batch 1, 4 x 128^3, eval mode ---------------------------------------------------------------
+    # ---- inference (cfg 2): batch 1, eval mode ---------------------------------------------------------------------
     inference = None
     if not args.no_inference:
         model.eval()
@@ -398,42 +465,47 @@ def main():
                 infer(x1)
             e1.record()
             barrier()
-        ims = e0.elapsed_time(e1) / args.steps
-        t = torch.tensor([ims], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ims = float(t.item())
+        ims = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         inference = {"value": world * 1e3 / ims, "unit": "volumes/s", "ms_per_volume": ims,
-                     "config": "batch 1 per GPU, 4x128^3, eval, bf16" + (", CUDA graph" if inf_graphed else ""),
-                     "conv_tflops": FWD_FLOP_PER_VOXEL * SIZE ** 3 / (ims * 1e-3) / 1e12}
+                     "config": "cfg2: batch 1 per GPU, 4x%dx%dx%d, eval, bf16%s" % (sd_, sh_, sw_, ", CUDA graph" if inf_graphed else ""),
+                     "conv_tflops": cfg["fwd_flop"] * vol / (ims * 1e-3) / 1e12}
+        if inf_graphed:
+            infer.close()
         model.train()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_train_steps(2, 1)
+        cb = cpu_train_steps(cfg, 2, 1)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "cfg3: train step, batch 2/GPU, 4x128^3, default arch [32,64,128,256,512], dropout 0.2, "
-                                   "DeepSupervisionLoss3D(CombinedLoss3D), step = fwd+loss+bwd(+NCCL grad all-reduce)+fused AdamW",
-                       "global_batch": world * PER_GPU_BATCH, "parallelism": "dp%d" % world, "cuda_graph": graphed,
-                       "l2": "no explicit flush: one step streams >5 GB of activations (>> 126 MB L2)"},
-            "conv_tflops_whole_step": TRAIN_FLOP_PER_VOXEL * vox_per_step / world / (ms / args.steps * 1e-3) / 1e12,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams, "bandwidth_families": bw_fams,
-            "inference": inference, "cpu_baseline": cpu_baseline,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": line_cfg, "cuda_graph": graphed,
+            "optimizer": type(opt).__name__,
+            "conv_tflops_whole_step": cfg["train_flop"] * vox_per_step / world / (ms / args.steps * 1e-3) / 1e12,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_families": fams,
+            "bandwidth_families": bw_fams, "inference": inference, "cpu_baseline": cpu_baseline,
         }
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:
         barrier()
-        if graphed:   # tearing down NCCL while a captured graph still references its streams hangs: leave without it
+        if graphed:   # a captured graph holds NCCL work: release it before the communicator goes away
+            step.close()
+        barrier()
+        done = threading.Event()
+
+        def _teardown():
+            dist.destroy_process_group()
+            done.set()
+        th = threading.Thread(target=_teardown, daemon=True)
+        th.start()
+        if not done.wait(30.0):   # never hang the launcher on communicator teardown
+            sys.stderr.write("[bench] rank %d: destroy_process_group did not return in 30 s; exiting\n" % rank)
             sys.stderr.flush()
             os._exit(0)
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -19,8 +19,20 @@ import torch.nn.functional as F
 REF = os.environ.get("B3D_REFERENCE_DIR", "/root/reference")
 
 
+MATERIALISED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_classes.py")
+
+
 def available():
-    return os.path.exists(os.path.join(REF, "main.py"))
+    """True when the reference's own classes can be executed: /root/reference is mounted (build container) or oracle/_ref/ was
+    materialised from it by oracle/make_ref.py (git-ignored, travels to the GPU box with the gpurun snapshot)."""
+    return os.path.exists(os.path.join(REF, "main.py")) or os.path.exists(MATERIALISED)
+
+
+def _load_materialised():
+    spec = importlib.util.spec_from_file_location("_b3d_ref_classes", MATERIALISED)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return {k: getattr(mod, k) for k in dir(mod) if not k.startswith("__")}
 
 
 def _class_block(src, name):
@@ -35,6 +47,8 @@ def _class_block(src, name):
 def load():
     """Returns a namespace dict with UNet3D, DoubleConv3D, AttentionGate3D (main.py), CombinedLoss3D, TverskyLoss3D,
     DeepSupervisionLoss3D (losses.py), CombinedLoss, DiceLoss, FocalLoss (training.py) and calculate_dice_score."""
+    if not os.path.exists(os.path.join(REF, "main.py")):
+        return _load_materialised()
     ns = {"torch": torch, "nn": nn, "F": F, "np": np}
     main_src = open(os.path.join(REF, "main.py")).read()
     for cls in ("DoubleConv3D", "AttentionGate3D", "UNet3D", "BrainTumorClassifier"):

@@ -82,8 +82,8 @@ def double_conv_fwd(x, p, pre, cin_real, need_bwd):
     if has_res_conv:   # the residual projection only depends on x: a side branch that overlaps with the 3x3x3 convs
         wrp, _, rowsr = packed(p[pre + "residual.0.weight"], ops.PACK_FPROP)
         with ops.side_branch(ops.BRANCH_MASK & 1, x) as br:
-            r, st_r = ops.conv_fprop(x, wrp, rowsr, cout, 1, groups=8)
-    y1, st1 = ops.conv_fprop(x, w1p, rows1, cout, 3, groups=8)
+            r, st_r = ops.conv_fprop(x, wrp, rowsr, cout, 1, groups=8, cin_real=cin_real)
+    y1, st1 = ops.conv_fprop(x, w1p, rows1, cout, 3, groups=8, cin_real=cin_real)
     a1 = ops.gn_apply(y1, st1, p[pre + "double_conv.1.weight"], p[pre + "double_conv.1.bias"], 8, True)
     w2p, _, rows2 = packed(w2, ops.PACK_FPROP)
     y2, st2 = ops.conv_fprop(a1, w2p, rows2, cout, 3, groups=8)

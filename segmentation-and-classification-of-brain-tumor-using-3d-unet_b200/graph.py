@@ -9,7 +9,13 @@ on static input buffers and replays it; the trainer call sites (training.py:290-
         loss = step(images, masks)          # device tensor; read it with .item() only when you need the number
 
 Everything the step launches (libb3d kernels, memsets, torch's fused AdamW, NCCL all-reduces) is stream-ordered and free of
-host synchronisation, which is what makes it capturable.  The optimizer must be constructed with capturable=True.
+host synchronisation, which is what makes it capturable.  The optimizer must be constructed with capturable=True, and its
+learning rate must live in a DEVICE tensor: a python-float lr is baked into the captured kernels, so a scheduler
+(`CosineAnnealingWarmRestarts`, training.py:195,252) would silently become a no-op behind the replayed graph.  A float lr
+is therefore replaced by a CUDA scalar tensor before the capture (torch's schedulers `fill_` a tensor lr in place).
+Loss scaling: the path computes in bf16 (fp32 exponent range), so `GradScaler` is unnecessary; the reference's literal
+`autocast` + `scaler.scale(loss).backward()` + `scaler.step()` sequence (training.py:292-299) works on the EAGER path
+(tests/test_gpu_trainer_loop.py) but is not captured here (`scaler.step` reads the inf flag on the host).
 """
 import torch
 
@@ -19,6 +25,11 @@ from . import functional, ops
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        for group in optimizer.param_groups:   # see the module doc: the lr must be a device scalar or schedulers stop working
+            if not torch.is_tensor(group["lr"]):
+                group["lr"] = torch.tensor(float(group["lr"]), dtype=torch.float32, device=example_x.device)
+            elif not group["lr"].is_cuda:
+                group["lr"] = group["lr"].to(example_x.device)
         self.x = example_x.detach().clone()
         self.y = example_y.detach().clone()
         self.graph = torch.cuda.CUDAGraph()
@@ -56,6 +67,13 @@ class GraphedTrainStep:
         functional.clear_pack_cache()   # parameters changed behind the version counters: eager calls must re-pack
         return self.loss
 
+    def close(self):
+        """Release the captured graph (and the NCCL work it holds) — call before `destroy_process_group()`."""
+        torch.cuda.synchronize()
+        self.graph.reset()
+        self.graph = None
+        functional.clear_pack_cache()
+
     # -- input pipelining: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes ----------
     def prefetch(self, x_host, y_host):
         """Start copying the NEXT batch (pinned host tensors) into staging buffers on a side stream."""
@@ -86,7 +104,10 @@ class GraphedTrainStep:
 class GraphedInference:
     """Eval-mode forward (main.py:390-393 / train_model.py:216-217 call sites) captured once and replayed:
         infer = GraphedInference(model, volume);  logits = infer(volume)   # static output buffer, fp32 NCDHW
-    The bf16 packed weights are frozen at capture time (serving); call `refresh()` after the parameters changed."""
+    The bf16 packed weights are frozen at capture time (serving); call `refresh()` after the parameters changed.  The graph
+    OWNS those packed copies: the captured kernels hold raw pointers into them, so the instance keeps a reference to every
+    packed tensor it captured — a later cache miss of `functional.packed` (optimizer step, `clear_pack_cache()`, a second
+    GraphedInference on the same model) replaces the per-parameter cache entries but can no longer free these buffers."""
 
     def __init__(self, model, example_x, warmup=3):
         assert not model.training, "GraphedInference captures the eval-mode forward"
@@ -111,6 +132,12 @@ class GraphedInference:
             self.out = self.model(self.x)
         ops.reset_scratch()
         torch.cuda.synchronize()
+        self._packs = [entry for prm in self.model.parameters() for entry in prm.__dict__.get("_b3d_pack", {}).values()]
+
+    def close(self):
+        torch.cuda.synchronize()
+        self.graph.reset()
+        self.graph, self._packs = None, None
 
     def __call__(self, x):
         if x is not self.x:

@@ -177,10 +177,12 @@ def pack_weight_pair(w, conv_transpose):
 # ---------------------------------------------------------------------------------------------------------------
 # tcgen05 convolutions
 # ---------------------------------------------------------------------------------------------------------------
-def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=False, out=None, cin=None, add=None):
+def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=False, out=None, cin=None, add=None,
+               cin_real=None):
     """y = conv(x) (+bias) (+add); optional GroupNorm (per sample) or BatchNorm (stats_batch) partial sums of y.
     `cin`: number of leading channels of x to contract over (multiple of 16; defaults to all).
-    `add`: NDHWC bf16 tensor summed into the result in the epilogue (1x1x1 only; may be `out` itself)."""
+    `add`: NDHWC bf16 tensor summed into the result in the epilogue (1x1x1 only; may be `out` itself).
+    `cin_real`: channels of x that are not zero padding — only used to count ALGORITHMIC FLOPs for bench.py's roofline."""
     n, d, h, w, c = x.shape
     cin = c if cin is None else cin
     dev = x.device
@@ -193,7 +195,7 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
     one = n * d * h * w * cout * 4
     ws_bytes = one * 16 if (one * 16 <= (1 << 26) and add is None) else 0
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
-    with _prof("igemm", 2.0 * n * d * h * w * cin * cout * ks ** 3, "conv%d %dx%dx%dx%d %d->%d" % (ks, n, d, h, w, cin, cout)):
+    with _prof("igemm", 2.0 * n * d * h * w * (cin if cin_real is None else cin_real) * cout * ks ** 3, "conv%d %dx%dx%dx%d %d->%d" % (ks, n, d, h, w, cin, cout)):
         check(_L().b3d_conv_fprop_add(ptr(x), c_ll(ld(x)), ptr(wpack), c_int(w_rows), ptr(bias), ptr(add),
                                   c_ll(ld(add) if add is not None else 0), ptr(out), c_ll(ld(out)),
                                   c_int(n), c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), c_int(ks), ptr(stats),
@@ -694,12 +696,24 @@ def loss_cfg(w_dice=0.0, smooth=1e-5, w_focal=0.0, f_alpha=0.25, f_gamma=2.0, w_
                                  tv_smooth)
 
 
+def _check_target(target, shape, device, who):
+    """The kernels read labels as `const long long*`: anything else would be read out of bounds.  The reference
+    (`F.one_hot` / `F.cross_entropy`, losses.py:20,31) raises for non-int64 labels too."""
+    if target.dtype != torch.int64:
+        raise _lib.B3DError("%s: target must be int64 class indices (got %s)" % (who, target.dtype))
+    if target.device != device:
+        raise _lib.B3DError("%s: target is on %s, logits on %s" % (who, target.device, device))
+    if tuple(target.shape) != tuple(shape):
+        raise _lib.B3DError("%s: target shape %s does not match logits' [N,D,H,W] = %s" % (who, tuple(target.shape), tuple(shape)))
+    return target.contiguous()
+
+
 def loss_fwd(logits, target, cfg):
     """Returns (values[6] = total,dice,focal,boundary,ce,tversky ; saved tuple for loss_bwd)."""
     n, k, d, h, w = logits.shape
     dev = logits.device
     logits = logits.contiguous()
-    target = target.contiguous()
+    target = _check_target(target, (n, d, h, w), dev, "loss")
     prob = torch.empty_like(logits)
     need_e = cfg[6] != 0.0
     e = torch.empty_like(logits) if need_e else None
@@ -728,7 +742,7 @@ def confusion(logits, target=None, want_mask=False):
         logits = logits.float()
     hist = torch.zeros((k, k), dtype=torch.int64, device=dev)
     mask = torch.empty((n, d, h, w), dtype=torch.uint8, device=dev) if want_mask else None
-    tgt = target.contiguous() if target is not None else None
+    tgt = _check_target(target, (n, d, h, w), dev, "metric") if target is not None else None
     check(_L().b3d_confusion(ptr(logits), ptr(tgt), ptr(mask), ptr(hist), c_int(n), c_int(k), c_ll(d * h * w), stream_ptr()))
     return hist, mask
 

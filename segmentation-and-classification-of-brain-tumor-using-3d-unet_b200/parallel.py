@@ -108,6 +108,8 @@ class DataParallel(torch.nn.Module):
         if broadcast_parameters and dist.is_initialized() and dist.get_world_size(process_group) > 1:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)
+            from . import functional   # `.data` writes bump no version counter: drop bf16 packs made before the broadcast
+            functional.clear_pack_cache()
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)

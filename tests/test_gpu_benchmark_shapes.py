@@ -1,0 +1,111 @@
+"""Parity at the shapes the benchmark numbers are quoted on (BASELINE.json configs 2, 3 and 5) — VERDICT r1 item 1.
+
+  * cfg 3: default architecture [32..512], train step on 2 x 4 x 128^3 with Dropout3d masks, DeepSupervisionLoss3D
+  * cfg 2: the same model, eval forward of 1 x 4 x 128^3 (+ argmax mask / metric kernels on those logits)
+  * cfg 5: wide architecture [64..1024] (config.py:139) on a 1 x 4 x 32x64x96 volume — non-16-multiple widths at the deep
+           levels (W = 48, 24, 12, 6, 3), C = 2048 concat at the bottom of the decoder
+  * batch 4 (cfg 4 runs 16/N volumes per GPU): 4 x 4 x 64^3
+
+The fp32 truth is the oracle (oracle/unet3d_oracle.py, pinned to the reference's own outputs by tests/golden) executed on the
+GPU in true fp32 (TF32 off): the CPU needs ~17 s per 128^3 volume for the same arithmetic.  Tolerances: parity_util.py.
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import b3d  # noqa: F401
+    import unet3d_b200 as U
+
+from oracle import unet3d_oracle as O
+from parity_util import DEV, REPORT, check_grads, exact_fp32, oracle_autocast_grads, oracle_train, rel_l2
+
+DEFAULT = (32, 64, 128, 256, 512)
+WIDE = (64, 128, 256, 512, 1024)
+
+
+def _model(feats, sd, dropout=0.0):
+    m = U.UNet3D(4, 4, features=list(feats), dropout_rate=dropout)
+    m.load_state_dict(sd)
+    return m.to(DEV)
+
+
+def _train_case(tag, feats, n, size, seed, dropout):
+    sd = O.make_state_dict(4, 4, feats, seed=seed)
+    x, y = O.make_inputs(n, size[0], size[1], size[2], seed=seed)
+    model = _model(feats, sd, dropout).train()
+    xd, yd = x.to(DEV), y.to(DEV)
+    torch.manual_seed(seed)
+    main, deep = model(xd)
+    # Dropout3d: the oracle replays the masks the model drew from torch's generator (their equality with F.dropout3d's own
+    # stream is pinned by test_unet_dropout_uses_torch_rng_stream)
+    masks = [m.cpu() for m in model._last_dropout_masks] if dropout > 0 else None
+    loss = U.DeepSupervisionLoss3D()((main, deep), yd)
+    loss.backward()
+    torch.cuda.synchronize()
+    rmain, rdeep, rloss, rgrads, rbn = oracle_train(sd, x, y, feats, masks=masks, device=DEV)
+    r = rel_l2(main.detach().cpu(), rmain)
+    REPORT[tag + "_logits_rel_l2"] = r
+    assert r <= 2.5e-2, r
+    for i in range(3):   # the 4th deep map is computed but never used by the loss (losses.py:118-124)
+        assert rel_l2(deep[i].detach().cpu(), rdeep[i]) <= 2.5e-2, i
+    REPORT[tag + "_loss"] = (float(loss), rloss)
+    assert abs(float(loss) - rloss) <= 1.5e-2 * abs(rloss), (float(loss), rloss)
+    agree = float((main.detach().argmax(1).cpu() == rmain.argmax(1)).float().mean())
+    REPORT[tag + "_argmax_agree"] = agree
+    assert agree >= 0.97, agree
+    check_grads(model, rgrads, tag, oracle_autocast_grads(sd, x, y, feats, masks=masks))
+    np.testing.assert_allclose(model.final_conv[1].running_mean.cpu().numpy(), rbn[0].numpy(), rtol=2e-2, atol=2e-3)
+    np.testing.assert_allclose(model.final_conv[1].running_var.cpu().numpy(), rbn[1].numpy(), rtol=2e-2, atol=2e-3)
+    assert int(model.final_conv[1].num_batches_tracked) == 1
+    print("REPORT", json.dumps({k: v for k, v in REPORT.items() if k.startswith(tag)}, default=str))
+    return model, sd, x, y
+
+
+def test_cfg3_train_step_2x4x128_default_arch_with_dropout():
+    """The headline configuration itself: 2 x 4 x 128^3, default architecture, Dropout3d(0.2) masks, deep supervision."""
+    _train_case("cfg3_128", DEFAULT, 2, (128, 128, 128), seed=31, dropout=0.2)
+
+
+def test_cfg2_inference_1x4x128_default_arch_and_metric_kernels():
+    """Eval forward at 1 x 4 x 128^3 vs the fp32 oracle; the argmax mask, confusion histogram, Dice score and voxel counts the
+    metric kernels derive from OUR fp32 logits are bit-exact against the oracle's integer arithmetic on the same logits."""
+    feats = DEFAULT
+    sd = O.make_state_dict(4, 4, feats, seed=32)
+    x, y = O.make_inputs(1, 128, 128, 128, seed=32)
+    model = _model(feats, sd).eval()
+    with torch.no_grad():
+        ev = model(x.to(DEV))
+        sdd = {k: v.to(DEV) for k, v in sd.items()}
+        with exact_fp32():
+            ev_ref, _, _ = O.unet_forward(x.to(DEV), sdd, feats, training=False)
+    assert ev.shape == (1, 4, 128, 128, 128) and ev.dtype == torch.float32
+    r = rel_l2(ev.cpu(), ev_ref.cpu())
+    REPORT["cfg2_128_logits_rel_l2"] = r
+    assert r <= 2.5e-2, r
+    agree = float((ev.argmax(1) == ev_ref.argmax(1)).float().mean())
+    REPORT["cfg2_128_argmax_agree"] = agree
+    assert agree >= 0.97, agree
+    # integer outputs: bit-exact on identical logits (2.1 M voxels: fp32 counts are still exact, < 2^24 per class)
+    mask, logits = U.segment(model, x.to(DEV), return_logits=True)
+    assert torch.equal(logits, ev), "eval forward is not reproducible"
+    assert torch.equal(mask.long().cpu(), ev.argmax(1).cpu())
+    assert torch.equal(U.confusion_matrix(ev, y.to(DEV)).cpu(), O.confusion_counts(ev.cpu(), y))
+    assert abs(U.calculate_dice_score(ev, y.to(DEV)) - O.dice_score(ev.cpu(), y)) < 1e-7
+    tumour, per_class, per_slice = O.voxel_counts(mask[0].cpu())
+    assert U.tumor_volumes(mask[0]) == {"tumor_voxels": tumour, "class_voxels": per_class, "slice_voxels": per_slice}
+    print("REPORT", json.dumps({k: v for k, v in REPORT.items() if k.startswith("cfg2")}, default=str))
+
+
+def test_cfg5_wide_model_ragged_volume():
+    """features = [64,128,256,512,1024] (HighQuality, config.py:139) on 1 x 4 x 32x64x96: ragged W at every deep level."""
+    _train_case("cfg5_wide", WIDE, 1, (32, 64, 96), seed=33, dropout=0.0)
+
+
+def test_batch4_64cubed_default_arch():
+    """Batch > 2 (cfg 4 puts up to 16 volumes on one GPU): 4 x 4 x 64^3, default architecture."""
+    _train_case("batch4_64", DEFAULT, 4, (64, 64, 64), seed=34, dropout=0.2)

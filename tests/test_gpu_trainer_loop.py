@@ -1,0 +1,224 @@
+"""The reference trainer's LITERAL call sequence on the B200 path:
+
+    /root/reference/training.py:290-309
+        optimizer.zero_grad()
+        with torch.cuda.amp.autocast():
+            outputs = model(images); loss = criterion(outputs, masks)
+        scaler.scale(loss).backward(); scaler.step(optimizer); scaler.update()
+        dice = calculate_dice_score(outputs, masks)
+
+plus the graph wrappers the bench's numbers come from: GraphedInference == eager bit-for-bit (and survives pack-cache churn),
+GraphedTrainStep.prefetch/step_prefetched == __call__, a scheduler step changes the update under replay, and the NCCL
+data-parallel equivalence check (2 GPUs, skipped on a 1-GPU box).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import b3d  # noqa: F401
+    import unet3d_b200 as U
+    from unet3d_b200 import functional
+
+from oracle import unet3d_oracle as O
+from parity_util import DEV, exact_fp32
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FEATS = (16, 32, 64, 128, 256)
+
+
+def _model(sd, dropout=0.0, feats=FEATS):
+    m = U.UNet3D(4, 4, features=list(feats), dropout_rate=dropout)
+    m.load_state_dict(sd)
+    return m.to(DEV)
+
+
+def test_reference_trainer_loop_autocast_gradscaler_adamw_dice():
+    """3 iterations of training.py:290-309 verbatim (autocast + GradScaler + AdamW(lr, wd=1e-4) + calculate_dice_score) against
+    the fp32 oracle running the same loop without a scaler (loss scaling is a mathematical no-op when nothing overflows)."""
+    sd = O.make_state_dict(4, 4, FEATS, seed=41)
+    x, y = O.make_inputs(2, 32, 32, 32, seed=41)
+    lr, steps = 2e-3, 3
+    # ---- oracle: fp32, plain AdamW, Dice from its own logits
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    osd = {k: v.clone() for k, v in sd.items()}
+    osd.update(params)
+    oopt = torch.optim.AdamW(list(params.values()), lr=lr, weight_decay=1e-4, betas=(0.9, 0.999))
+    ref_loss, ref_dice = [], []
+    for _ in range(steps):
+        oopt.zero_grad()
+        main, deep, _ = O.unet_forward(x, osd, FEATS, training=True)
+        loss = O.deep_supervision_loss(main, deep, y)
+        loss.backward()
+        oopt.step()
+        ref_loss.append(float(loss.detach()))
+        ref_dice.append(O.dice_score(main.detach(), y))
+    # ---- B200 path: the trainer's literal sequence
+    model = _model(sd).train()
+    criterion = U.DeepSupervisionLoss3D()
+    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=1e-4, betas=(0.9, 0.999))   # training.py:186-191
+    scaler = torch.cuda.amp.GradScaler()                                                             # training.py:199
+    images, masks = x.to(DEV), y.to(DEV)
+    got_loss, got_dice = [], []
+    for _ in range(steps):
+        optimizer.zero_grad()
+        with torch.cuda.amp.autocast():
+            outputs = model(images)
+            loss = criterion(outputs, masks)
+        scaler.scale(loss).backward()
+        scaler.step(optimizer)
+        scaler.update()
+        dice = U.calculate_dice_score(outputs[0], masks)
+        got_loss.append(loss.item())
+        got_dice.append(dice)
+        assert isinstance(dice, float) and 0.0 <= dice <= 1.0
+        # the metric kernel is integer-exact on the logits it was given
+        assert abs(dice - O.dice_score(outputs[0].detach().cpu(), y)) < 1e-7
+    assert scaler.get_scale() == 65536.0, "GradScaler saw an inf/nan and backed off: %s" % scaler.get_scale()
+    for i, (a, b) in enumerate(zip(ref_loss, got_loss)):
+        assert abs(a - b) <= 1.5e-2 * abs(a), "step %d: oracle %s vs b200 %s" % (i, ref_loss, got_loss)
+    assert got_loss[-1] < got_loss[0]
+    for a, b in zip(ref_dice, got_dice):   # Dice of near-random logits: flips of near-ties move it by a few 1e-3
+        assert abs(a - b) <= 2e-2, (ref_dice, got_dice)
+
+
+def test_trainer_combined_loss_on_eval_output_under_autocast():
+    """validate_epoch (training.py:332-339): eval forward -> training.CombinedLoss -> calculate_dice_score, under no_grad."""
+    sd = O.make_state_dict(4, 4, FEATS, seed=42)
+    x, y = O.make_inputs(1, 32, 32, 32, seed=42)
+    model = _model(sd).eval()
+    with torch.no_grad():
+        out = model(x.to(DEV))
+        loss = U.CombinedLoss()(out, y.to(DEV))
+        ref = O.trainer_combined_loss(out.cpu(), y)
+    assert abs(loss.item() - float(ref)) < 2e-5
+    assert abs(U.calculate_dice_score(out, y.to(DEV)) - O.dice_score(out.cpu(), y)) < 1e-7
+
+
+def test_graphed_inference_is_bitwise_eager_and_owns_its_weights():
+    """the captured kernels point at packed bf16 weights; a later cache miss must not free them."""
+    sd = O.make_state_dict(4, 4, FEATS, seed=43)
+    x, _ = O.make_inputs(1, 32, 32, 32, seed=43)
+    x2, _ = O.make_inputs(1, 32, 32, 32, seed=44)
+    model = _model(sd).eval()
+    xd, x2d = x.to(DEV), x2.to(DEV)
+    with torch.no_grad():
+        want, want2 = model(xd).clone(), model(x2d).clone()
+    infer = U.GraphedInference(model, xd)
+    assert torch.equal(infer(xd), want)
+    assert torch.equal(infer(x2d), want2)
+    # churn: invalidate the pack cache, run eager forwards (re-pack -> the cache entries are REPLACED), a second graph on
+    # another volume size, and enough allocations to recycle any freed block
+    functional.clear_pack_cache()
+    with torch.no_grad():
+        model(x2d)
+    big, _ = O.make_inputs(1, 64, 32, 32, seed=45)
+    infer_b = U.GraphedInference(model, big.to(DEV))
+    junk = [torch.randn(1 << 20, device=DEV) for _ in range(64)]
+    junk = [torch.full((n,), 7.0, device=DEV, dtype=torch.bfloat16) for n in (1 << 12, 1 << 16, 1 << 20, 1 << 22) for _ in range(8)]
+    torch.cuda.synchronize()
+    assert torch.equal(infer(xd), want), "replay after pack-cache churn differs (graph read freed weights)"
+    with torch.no_grad():
+        assert torch.equal(infer_b(big.to(DEV)), model(big.to(DEV)))
+    del junk
+    # refresh() picks up changed parameters
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.01)
+        want3 = model(xd).clone()
+    assert not torch.equal(want3, want)
+    infer.refresh()
+    assert torch.equal(infer(xd), want3)
+    infer.close(); infer_b.close()
+
+
+def _fresh_graph_step(sd, xd, yd, lr):
+    model = _model(sd).train()
+    crit = U.DeepSupervisionLoss3D()
+    opt = U.make_adamw(model, lr=lr, weight_decay=1e-4, capturable=True)
+    step = U.GraphedTrainStep(model, crit, opt, xd, yd, warmup=1)
+    model.load_state_dict(sd)                      # undo the warm-up / capture optimizer steps
+    for st in opt.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    return model, opt, step
+
+
+def test_prefetch_pipeline_equals_direct_call():
+    """GraphedTrainStep.prefetch/step_prefetched (the e2e path of bench.py: pinned host -> staging on a copy stream ->
+    static buffers -> replay) produces exactly the losses of __call__ on the same batches."""
+    sd = O.make_state_dict(4, 4, FEATS, seed=46)
+    batches = [O.make_inputs(2, 32, 32, 32, seed=50 + i) for i in range(3)]
+    x0, y0 = batches[0]
+    out = {}
+    for mode in ("call", "prefetch"):
+        model, opt, step = _fresh_graph_step(sd, x0.to(DEV), y0.to(DEV), 1e-3)
+        losses = []
+        if mode == "call":
+            for xb, yb in batches:
+                losses.append(float(step(xb.to(DEV), yb.to(DEV))))
+        else:
+            pinned = [(xb.pin_memory(), yb.pin_memory()) for xb, yb in batches]
+            step.prefetch(*pinned[0])
+            for i in range(len(pinned)):
+                lt = step.step_prefetched()
+                if i + 1 < len(pinned):
+                    step.prefetch(*pinned[i + 1])
+                losses.append(lt.item())
+        out[mode] = losses
+        step.close()
+    for a, b in zip(out["call"], out["prefetch"]):
+        assert abs(a - b) <= 2e-4 * abs(a), out   # same kernels, same order: only the fp32-atomic jitter of the wgrad flush
+
+
+def test_scheduler_changes_the_update_under_graph_replay():
+    """a python-float lr is baked into a captured optimizer; GraphedTrainStep keeps the lr in a device
+    tensor so CosineAnnealingWarmRestarts (training.py:194-196,252) keeps working behind the replayed graph."""
+    sd = O.make_state_dict(4, 4, FEATS, seed=47)
+    x, y = O.make_inputs(1, 32, 32, 32, seed=47)
+    xd, yd = x.to(DEV), y.to(DEV)
+    model = _model(sd).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.0, fused=True, capturable=True)   # FLOAT lr on purpose
+    step = U.GraphedTrainStep(model, U.DeepSupervisionLoss3D(), opt, xd, yd, warmup=1)
+    assert torch.is_tensor(opt.param_groups[0]["lr"]) and opt.param_groups[0]["lr"].is_cuda
+    sched = U.make_scheduler(opt, T_0=2, T_mult=1, eta_min=1e-6)
+    w = model.downs[0].double_conv[0].weight
+    deltas, lrs = [], []
+    for _ in range(4):
+        before = w.detach().clone()
+        step(xd, yd)
+        torch.cuda.synchronize()
+        deltas.append(float((w.detach() - before).abs().max()))
+        lrs.append(float(opt.param_groups[0]["lr"]))
+        sched.step()
+    # T_0 = 2: lr alternates 1e-3, ~5e-4, 1e-3, ~5e-4; Adam's update magnitude ~ lr per element
+    assert abs(lrs[0] - 1e-3) < 1e-9 and abs(lrs[1] - 5.005e-4) < 1e-6 and abs(lrs[2] - 1e-3) < 1e-9, lrs
+    assert deltas[1] < 0.75 * deltas[0] and deltas[2] > 1.3 * deltas[1], (deltas, lrs)
+    step.close()
+
+
+def test_loss_and_metric_reject_non_int64_targets():
+    logits = torch.randn(1, 4, 8, 8, 8, device=DEV)
+    for bad in (torch.zeros(1, 8, 8, 8, dtype=torch.uint8, device=DEV), torch.zeros(1, 8, 8, 8, dtype=torch.int32, device=DEV),
+                torch.zeros(1, 8, 8, 4, dtype=torch.int64, device=DEV), torch.zeros(1, 8, 8, 8, dtype=torch.int64)):
+        with pytest.raises(Exception):
+            U.CombinedLoss3D()(logits, bad)
+        with pytest.raises(Exception):
+            U.calculate_dice_score(logits, bad)
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL)")
+def test_data_parallel_gradients_equal_mean_of_local_gradients_nccl():
+    """scripts/dp_check.py under torchrun, 2 ranks over NCCL: the gradients DataParallel leaves in .grad equal the mean of the
+    ranks' local gradients (whole model 1e-4, worst tensor max(1e-4, 10 x run-to-run jitter))."""
+    env = dict(os.environ, DP_CHECK_SIZE="32", MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "scripts", "dp_check.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

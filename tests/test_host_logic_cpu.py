@@ -95,3 +95,17 @@ def test_zeros_scratch_and_side_branch_are_inert_on_cpu():
         z += 1
     br.join()
     assert float(z.sum()) == 12.0
+
+
+def test_seed0_init_is_bit_identical_to_the_reference(golden):
+    """Same constructor tree / registration order / init calls as main.py:102-153 => the same torch seed yields bit-identical
+    initial parameters and buffers (hashes of the reference's own state_dict, tests/golden/make_golden.py:init_case)."""
+    import hashlib
+    import unet3d_b200 as U
+    torch.manual_seed(0)
+    m = U.UNet3D(4, 4, features=[16, 32, 64, 128, 256])
+    want = golden["init_small"]
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(want.keys())
+    for k, v in sd.items():
+        assert hashlib.sha1(v.numpy().tobytes()).hexdigest()[:16] == want[k], k
