@@ -23,7 +23,11 @@ extern "C" {
 int b3d_version(void);
 const char* b3d_last_error_string(void);             /* thread-local */
 int b3d_check_device(void);                          /* 0 iff current device is compute capability 10.x */
-long long b3d_launch_count(void);                    /* kernels launched by this library so far (process-wide) */
+long long b3d_launch_count(void);                    /* kernels launched by this library so far (process-wide, atomic) */
+/* 1: ONE MMA-issuing warp instead of two ping-pong issuers in the z-marching 3x3x3 kernel -> fixed fp32 accumulation order ->
+ * the forward pass and the input gradients are bit-reproducible run to run (default 0, or env B3D_ORDERED_ISSUE; the
+ * reference's cuDNN path makes no such promise either).  Returns the previous setting.  Process-wide, atomic. */
+int b3d_set_ordered_issue(int on);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_igemm.cu, conv_wgrad.cu) ----------------------------------- */
 /* weight repack fp32 reference layout -> bf16 [K/8][taps][rows][8].
@@ -118,6 +122,9 @@ int b3d_ds_head_fwd(const void* x, long long ldx, const float* w, const float* b
                     void* stream);
 int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
                     int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream);
+/* same, logit gradient channel-last: dl float [N][Vs][4] (what b3d_dsloss_bwd produces) */
+int b3d_ds_head_bwd_cl(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
+                       int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream);
 int b3d_trilinear_up_fwd(const float* lo, float* out, int N, int Dl, int Hl, int Wl, int D, int H, int W, int K,
                          void* stream);
 int b3d_trilinear_up_bwd(const float* dup, float* dlo, float* tmp, int N, int Dl, int Hl, int Wl, int D, int H, int W,
@@ -137,6 +144,16 @@ int b3d_loss_fwd(const float* logits, const long long* target, const float* cfg1
                  float* values, int N, int K, int D, int H, int W, void* stream);
 int b3d_loss_bwd(const float* prob, const float* E, const long long* target, const double* acc, const float* cfg11,
                  const float* gscale, float wscale, float* dlogits, int N, int K, int D, int H, int W, void* stream);
+/* ---- fused deep-supervision loss (dsloss.cu): F.interpolate(trilinear) main.py:165-170 + CombinedLoss3D.forward
+ *      losses.py:63-75 as evaluated per output by DeepSupervisionLoss3D.forward losses.py:107-126, computed from the LOW-RES
+ *      head logits (float4 [N][D/s][H/s][W/s], s in {1,2,4,8}) without materialising the up-sampled map.
+ *      target_u8: labels as uint8 [N][D][H][W] (b3d_target_u8; anything outside 0..3 -> 255 = matches no class).
+ *      dlo: s == 1 float [N][V][4]; s > 1 double [N][V/s^3][4] (zeroed inside, fp64 atomics). ------------------------- */
+int b3d_target_u8(const long long* target, unsigned char* out, long long count, void* stream);
+int b3d_dsloss_fwd(const float* lo, const unsigned char* target_u8, const float* cfg11, double* acc, float* values, int N,
+                   int scale, int D, int H, int W, void* stream);
+int b3d_dsloss_bwd(const float* lo, const unsigned char* target_u8, const double* acc, const float* cfg11, const float* gscale,
+                   float wscale, void* dlo, int N, int scale, int D, int H, int W, void* stream);
 int b3d_confusion(const float* logits, const long long* target, unsigned char* mask, unsigned long long* hist, int N,
                   int K, long long V, void* stream);
 int b3d_voxel_counts(const unsigned char* mask, long long V, int W, unsigned long long* cls, unsigned long long* slices,

@@ -66,3 +66,9 @@ def require_device(device):
         with torch.cuda.device(device):
             check(lib().b3d_check_device())
         _DEVICE_OK[key] = True
+
+
+def set_ordered_issue(on):
+    """Bit-reproducible forward / input gradients (one MMA issuer in the z-marching conv kernel instead of two ping-pong
+    issuers, whose accumulation order jitters by an fp32 ulp from run to run).  Returns the previous setting."""
+    return bool(lib().b3d_set_ordered_issue(c_int(1 if on else 0)))

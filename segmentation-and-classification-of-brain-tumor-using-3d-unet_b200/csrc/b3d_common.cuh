@@ -39,7 +39,18 @@ void b3d_set_error(const char* fmt, ...);
   } while (0)
 
 int b3d_num_sms();
-extern long long g_b3d_launches;  // kernels launched by the library (bench.py reports it)
+// Debugging knobs are read from the environment ONCE per call site (function-local static: thread-safe, no getenv on the
+// launch path).
+#include <stdlib.h>
+#define B3D_ENV_FLAG(name) ([] { static const bool v_ = getenv(name) != nullptr; return v_; }())
+#define B3D_ENV_INT(name) ([] { static const int v_ = getenv(name) ? atoi(getenv(name)) : 0; return v_; }())
+// b3d_set_ordered_issue(1): one MMA-issuing warp instead of two ping-pong issuers in conv_zs.cu, which makes the fp32
+// accumulation order — hence the forward pass and the input gradients — bit-reproducible from run to run (default: env
+// B3D_ORDERED_ISSUE, else 0).
+#include <atomic>
+extern std::atomic<int> g_b3d_ordered_issue;
+#include <atomic>
+extern std::atomic<long long> g_b3d_launches;  // kernels launched by the library (bench.py reports it)
 
 // ---------------------------------------------------------------------------------------------
 // Small device utilities

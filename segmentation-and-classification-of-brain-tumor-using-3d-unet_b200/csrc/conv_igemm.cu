@@ -582,13 +582,13 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
   const int halo = ks / 2, KD = ks, KHW = ks * ks;
   const int Ktotal = chan_per_map * nmaps;
   IgemmPlan best; best.ok = false; best.cost = 1e30;
-  const int env_td = getenv("B3D_TD") ? atoi(getenv("B3D_TD")) : 0;
-  const int env_th = getenv("B3D_TH") ? atoi(getenv("B3D_TH")) : 0;
-  const int env_tw = getenv("B3D_TW") ? atoi(getenv("B3D_TW")) : 0;
-  const int env_kc = getenv("B3D_KC") ? atoi(getenv("B3D_KC")) : 0;
-  const int env_bn = getenv("B3D_BN") ? atoi(getenv("B3D_BN")) : 0;
+  const int env_td = B3D_ENV_INT("B3D_TD");
+  const int env_th = B3D_ENV_INT("B3D_TH");
+  const int env_tw = B3D_ENV_INT("B3D_TW");
+  const int env_kc = B3D_ENV_INT("B3D_KC");
+  const int env_bn = B3D_ENV_INT("B3D_BN");
   const int bn_cands[5] = {256, 128, 64, 32, 16};
-  for (int patch = getenv("B3D_NOPATCH") ? 0 : 1; patch >= 0; --patch) {
+  for (int patch = B3D_ENV_FLAG("B3D_NOPATCH") ? 0 : 1; patch >= 0; --patch) {
     // patch mode: tile = TD x (16 a) x (8 b), M-block = 16 rows x 8 columns (no wasted M rows)
     // linear mode: tile rows are TW wide (whole W when it fits), M-block = 128 consecutive halo-pitched positions
     for (int TD = 1; TD <= 16 && TD <= std::max(D, 1); TD *= 2)
@@ -644,7 +644,7 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
               const long long tiles = (long long)N * ((D + TD - 1) / TD) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
               const long long items = tiles * n_blocks;
               int ksplit = 1;
-              if (max_split > 1 && items * 2 <= num_sms && steps_total > 1 && !getenv("B3D_NOSPLIT")) {
+              if (max_split > 1 && items * 2 <= num_sms && steps_total > 1 && !B3D_ENV_FLAG("B3D_NOSPLIT")) {
                 ksplit = (int)std::min<long long>(std::min(steps_total, max_split), num_sms / items);
                 const int sps = (steps_total + ksplit - 1) / ksplit;
                 ksplit = (steps_total + sps - 1) / sps;
@@ -682,11 +682,8 @@ struct ActView {
 
 template <int BN, int KC>
 static int ig_launch(const IgParams& P, size_t smem, int grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  static const cudaError_t attr = cudaFuncSetAttribute(igemm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // one-time, thread-safe
+  B3D_CHECK_CUDA(attr);
   igemm_kernel<BN, KC><<<grid, IG_THREADS, smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
@@ -778,7 +775,7 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   const size_t smem = (size_t)P.stages * P.stage_bytes + std::max<size_t>((size_t)pl.over, 16 * IG_MAXSTAGES + 48 + 64 * 8 + 128) + 1024;
   B3D_REQUIRE(smem <= 227 * 1024, "igemm: smem %zu too large", smem);
   const int grid = std::min(P.num_items, num_sms);
-  if (getenv("B3D_VERBOSE"))
+  if (B3D_ENV_FLAG("B3D_VERBOSE"))
     fprintf(stderr,
             "[b3d] igemm N%d D%d H%d W%d K=%dx%d Cout=%d(ks%d mode%d) tile %dx%dx%d %s KC%d BN%d MB%d stages%d acc%d "
             "split%d items%d smem%zu tmem%d\n",

@@ -295,11 +295,8 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) wg2_kernel(const __grid_consta
 
 template <int GWX, int GWY, int KSTEPS>
 static int wg2_launch1(const Wg2Params& P, size_t smem, int grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(wg2_kernel<GWX, GWY, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  static const cudaError_t attr = cudaFuncSetAttribute(wg2_kernel<GWX, GWY, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // one-time, thread-safe
+  B3D_CHECK_CUDA(attr);
   wg2_kernel<GWX, GWY, KSTEPS><<<grid, WG2_THREADS, smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
@@ -320,7 +317,7 @@ static int wg2_launch(const Wg2Params& P, size_t smem, int grid, cudaStream_t st
 // dwacc: zeroed fp32 [27][Cin_pad][Cout_pad]; x exposes Cin (multiple of 16) channels, dy Cout_pad (multiple of 16).
 int b3d_try_wg2(const void* x, long long ldx, int Cin, const void* dy, long long lddy, int Cout_pad, int N, int D, int H, int W,
                 float* dwacc, int Cin_pad, int* err_flag, cudaStream_t stream) {
-  if (getenv("B3D_NO_WG2")) return 1;
+  if (B3D_ENV_FLAG("B3D_NO_WG2")) return 1;
   if (W % 16 || W < 16 || W + 2 > 256 || Cin % 16 || Cout_pad % 16) return 1;
   const int GWX = (Cin % 32 == 0) ? 32 : 16, GWY = (Cout_pad % 32 == 0) ? 32 : 16;
   const int RBX = GWX * 2, RBY = GWY * 2;
@@ -331,9 +328,9 @@ int b3d_try_wg2(const void* x, long long ldx, int Cin, const void* dy, long long
   int TH = 0, TW = 0, R = 0, RY = 0;
   size_t xs = 0, ys = 0;
   double best = -1;
-  const int env_th = getenv("B3D_WG2_TH") ? atoi(getenv("B3D_WG2_TH")) : 0;
-  const int env_tw = getenv("B3D_WG2_TW") ? atoi(getenv("B3D_WG2_TW")) : 0;
-  const int env_r = getenv("B3D_WG2_R") ? atoi(getenv("B3D_WG2_R")) : 0;
+  const int env_th = B3D_ENV_INT("B3D_WG2_TH");
+  const int env_tw = B3D_ENV_INT("B3D_WG2_TW");
+  const int env_r = B3D_ENV_INT("B3D_WG2_R");
   // measured (B3D_WG2_* sweeps, 2x128^3 32x32): full-width rows, the tallest tile and the minimal ring (R=4, RY=2) win —
   // the per-plane-tile fixed cost matters more than prefetch depth
   for (int tw = std::min(W, 128); tw >= 16; tw /= 2) {
@@ -382,7 +379,7 @@ int b3d_try_wg2(const void* x, long long ldx, int Cin, const void* dy, long long
   B3D_CHECK_CUDA(cudaMemsetAsync(dwacc, 0, (size_t)27 * Cin_pad * Cout_pad * 4, stream));
   const int num_sms = b3d_num_sms();
   const int grid = (int)std::min<long long>(num_sms, P.total_steps);
-  if (getenv("B3D_VERBOSE"))
+  if (B3D_ENV_FLAG("B3D_VERBOSE"))
     fprintf(stderr, "[b3d] wg2 N%d D%d H%d W%d Cin%d Cout%d GWX%d GWY%d TH%d TW%d R%d RY%d keys%d cols%d grid%d smem%zu\n", N, D, H,
             W, Cin, Cout_pad, GWX, GWY, TH, TW, R, RY, P.n_cib * P.n_cob, P.columns, grid, smem);
   if (GWX == 32 && GWY == 32) return wg2_launch<32, 32>(P, smem, grid, stream);

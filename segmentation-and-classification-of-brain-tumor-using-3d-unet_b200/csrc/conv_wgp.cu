@@ -205,11 +205,8 @@ __global__ void __launch_bounds__(WGP_THREADS, 1) wgp_kernel(const __grid_consta
 
 template <int GWX, int GWY>
 static int wgp_launch(const WgpParams& P, size_t smem, int grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(wgp_kernel<GWX, GWY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  static const cudaError_t attr = cudaFuncSetAttribute(wgp_kernel<GWX, GWY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // one-time, thread-safe
+  B3D_CHECK_CUDA(attr);
   wgp_kernel<GWX, GWY><<<grid, WGP_THREADS, smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
@@ -221,7 +218,7 @@ static int wgp_launch(const WgpParams& P, size_t smem, int grid, cudaStream_t st
 //   tap t8 = (a,b,c) reads dy[n, 2z+a, 2y+b, 2x+c].
 int b3d_try_wgp(const void* x, long long ldx, int Cin, const void* dy, long long lddy, int Cout_pad, long long V, int taps,
                 int ND, int Hc, int Wc, float* dwacc, int Cin_pad, int* err_flag, cudaStream_t stream) {
-  if (getenv("B3D_NO_WGP")) return 1;
+  if (B3D_ENV_FLAG("B3D_NO_WGP")) return 1;
   if (Cin % 16 || Cout_pad % 16 || V < 16 || (ldx * 2) % 16 || (lddy * 2) % 16) return 1;
   if (taps != 1 && taps != 8) return 1;
   const int GWX = (Cin % 32 == 0) ? 32 : 16, GWY = (Cout_pad % 32 == 0) ? 32 : 16;
@@ -299,7 +296,7 @@ int b3d_try_wgp(const void* x, long long ldx, int Cin, const void* dy, long long
   const int num_sms = b3d_num_sms();
   // at least ~4 K tiles per CTA so that a flush (up to 128 x 256 fp32 reductions) is amortised
   const int grid = (int)std::max<long long>(1, std::min<long long>(num_sms, P.total_steps / 4));
-  if (getenv("B3D_VERBOSE"))
+  if (B3D_ENV_FLAG("B3D_VERBOSE"))
     fprintf(stderr, "[b3d] wgp V%lld Cin%d Cout%d GWX%d GWY%d NB%d KT%d S%d keys%d tiles%lld grid%d smem%zu\n", V, Cin, Cout_pad,
             GWX, GWY, P.NB, KT, S, P.n_cib * P.n_cob, P.tiles, grid, smem);
   if (GWX == 32 && GWY == 32) return wgp_launch<32, 32>(P, smem, grid, stream);

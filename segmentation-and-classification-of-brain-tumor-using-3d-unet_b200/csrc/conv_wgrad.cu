@@ -357,7 +357,6 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
 // host
 // ---------------------------------------------------------------------------------------------
 static const int kWgSmemBudget = 227 * 1024 - 1024;
-static bool g_wg_attr = false;
 
 struct YView { const void* base; long long sW, sH, sND; };
 
@@ -454,7 +453,7 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
   if (P.items_per_cta % P.items_per_key != 0 && P.num_keys * 2 >= num_sms)
     P.items_per_cta = (P.items_per_cta + P.items_per_key - 1) / P.items_per_key * P.items_per_key;
   P.exclusive = (P.items_per_cta % P.items_per_key == 0) ? 1 : 0;
-  if (getenv("B3D_WG_NOEXCL")) P.exclusive = 0;
+  if (B3D_ENV_FLAG("B3D_WG_NOEXCL")) P.exclusive = 0;
   if (!P.exclusive)
     B3D_CHECK_CUDA(cudaMemsetAsync(dwacc, 0, (size_t)(ks == 3 ? 27 : (nmapsY > 1 ? nmapsY : 1)) * Cin_pad * Cout_pad * 4, stream));
   const int grid2 = (P.num_items + P.items_per_cta - 1) / P.items_per_cta;
@@ -498,11 +497,10 @@ static int run_wgrad(const void* x, long long ldx, int Cin_use, const YView* yv,
     int rc = b3d_encode_tmap_bf16(&P.tmY[m], yv[m].base, 5, dims, strides, box);
     if (rc) return rc;
   }
-  if (!g_wg_attr) {
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    g_wg_attr = true;
-  }
-  if (getenv("B3D_VERBOSE"))
+  static const cudaError_t wg_attr =   // one-time, thread-safe
+      cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  B3D_CHECK_CUDA(wg_attr);
+  if (B3D_ENV_FLAG("B3D_VERBOSE"))
     fprintf(stderr,
             "[b3d] wgrad N%d D%d H%d W%d Cin%d Cout%d ks%d variant%d plane%d ci_blk%d G%d BN%d chains%d TH%d TZ%d keys%d "
             "items%d (per cta %d) smem%zu tmem%d\n",

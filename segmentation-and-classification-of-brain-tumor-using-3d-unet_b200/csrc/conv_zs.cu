@@ -34,6 +34,7 @@ struct alignas(64) ZsParams {
   int N, D, H, W, Cout;
   int tiles_x, tiles_y, n_blocks, tiles_per_nb;  // column = nb * tiles_per_nb + ((n * tiles_y + ty) * tiles_x + tx)
   int k_chunks, stages;
+  int solo;               // 1: warp 1 issues every plane (bit-reproducible accumulation order), warp 6 idles
   long long total_steps;  // columns * D output planes
   bf16* out; long long ld_out;
   const float* bias;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     for (int i = 0; i < R; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
     mbar_init(wfull, 1);
-    mbar_init(wfree, 2);
+    mbar_init(wfree, P.solo ? 1 : 2);
     mbar_init(hs0, 1); mbar_init(hs0 + 8, 1);
     mbar_fence_init();
   }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
     const uint32_t role = (warp == 1) ? 0u : 1u;
     int cur_nb = -1;
     uint32_t wloads = 0;
-    long long pos = lo;
+    long long pos = (P.solo && role == 1u) ? hi : lo;   // ordered-issue mode: warp 6 idles
     ZsSeg sg;
     auto wait_fresh = [&](uint32_t g) {   // the epilogue has drained + zeroed the slot that plane g re-uses
       mbar_wait(tempty0 + 8 * (g & RM), (((g / R) & 1u) ^ 1u), P.err, 24);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
       // the other does the barrier waits / ring arithmetic of the next plane, then issues right behind it.  The tensor
       // pipe executes in issue order, so accumulations into shared ring slots stay ordered; hs[r] = "warp r has issued".
       for (int i = i_min; i <= i_max; ++i, ++pc) {
-        if ((pc & 1u) != role) {   // the other warp's plane: only keep the stage ring position in step
+        if (!P.solo && (pc & 1u) != role) {   // the other warp's plane: only keep the stage ring position in step
           for (int kc = 0; kc < P.k_chunks; ++kc) if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
           continue;
         }
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
         const uint32_t id2 = run2 == 2 ? idesc2 : idesc1;
         for (int kc = 0; kc < P.k_chunks; ++kc) {
           mbar_wait(full0 + 8 * s, ph, P.err, 23);
-          if (kc == 0 && pc > 0) mbar_wait(hs0 + 8 * (role ^ 1u), ((pc - 1u) >> 1) & 1u, P.err, 26);  // previous plane issued
+          if (!P.solo && kc == 0 && pc > 0) mbar_wait(hs0 + 8 * (role ^ 1u), ((pc - 1u) >> 1) & 1u, P.err, 26);  // previous plane issued
           tc_fence_after();
           const uint32_t a16 = ((sA + s * A_STAGE) >> 4) | LBO1;
           const uint32_t w16 = (((sW + kc * W_CHUNK) >> 4) + (uint32_t)(kd0 * COUT) * rb16) | LBO1;
@@ -397,11 +398,9 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
 
 template <int COUT, int KC>
 static int zs_launch(const ZsParams& P, size_t smem, int grid, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(zs_kernel<COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  static const cudaError_t attr =   // function-local static: initialised once, thread-safe
+      cudaFuncSetAttribute(zs_kernel<COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  B3D_CHECK_CUDA(attr);
   zs_kernel<COUT, KC><<<grid, ZS_THREADS, smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
@@ -412,12 +411,12 @@ static int zs_launch(const ZsParams& P, size_t smem, int grid, cudaStream_t stre
 int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
                int N, int D, int H, int W, int Cin, int Cout, double* stats, int cpg, int stats_groups, int stats_batch,
                int* err_flag, cudaStream_t stream) {
-  if (getenv("B3D_NO_ZS")) return 1;
+  if (B3D_ENV_FLAG("B3D_NO_ZS")) return 1;
   const int CoutPad = w_rows;
   if (CoutPad % 16 || Cin % 16) return 1;
   if (D < 2 || (long long)H * W < 256) return 1;
   const bool big_ok = (CoutPad <= 64) || (CoutPad == 128 && Cin <= 64);
-  if (!big_ok && !getenv("B3D_ZS_ALL")) return 1;
+  if (!big_ok && !B3D_ENV_FLAG("B3D_ZS_ALL")) return 1;
   const int KC = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   const int RB = KC * 2;
   const int k_chunks = Cin / KC;
@@ -425,7 +424,7 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
   const size_t aux_bytes = 16 * ZS_MAXSTAGES + 16 * 32 + 32 + 128 * 8 + 64;
   const size_t budget = 227 * 1024 - 1024 - aux_bytes;
   int COUT = 0, stages = 0;
-  const int forced = getenv("B3D_ZS_COUT") ? atoi(getenv("B3D_ZS_COUT")) : 0;
+  const int forced = B3D_ENV_INT("B3D_ZS_COUT");
   const int cands[3] = {64, 32, 16};
   for (int ci = 0; ci < 3; ++ci) {
     const int c = cands[ci];
@@ -451,6 +450,7 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
   P.tiles_x = (W + 7) / 8; P.tiles_y = (H + 15) / 16; P.n_blocks = CoutPad / COUT;
   P.tiles_per_nb = N * P.tiles_x * P.tiles_y;
   P.k_chunks = k_chunks; P.stages = stages;
+  P.solo = g_b3d_ordered_issue.load() ? 1 : 0;
   P.total_steps = (long long)P.tiles_per_nb * P.n_blocks * D;
   P.out = (bf16*)y; P.ld_out = ldy; P.bias = bias;
   P.stats = stats; P.cpg = cpg > 0 ? cpg : 16; P.stats_groups = stats_groups; P.stats_batch = stats_batch; P.err = err_flag;
@@ -472,7 +472,7 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
   if (smem > 227 * 1024) return 1;
   const int num_sms = b3d_num_sms();
   const int grid = (int)std::min<long long>(num_sms, P.total_steps);
-  if (getenv("B3D_VERBOSE"))
+  if (B3D_ENV_FLAG("B3D_VERBOSE"))
     fprintf(stderr, "[b3d] zs N%d D%d H%d W%d Cin%d Cout%d COUT%d KC%d chunks%d stages%d nblk%d cols%d grid%d smem%zu\n", N, D, H,
             W, Cin, Cout, COUT, KC, k_chunks, stages, P.n_blocks, P.tiles_per_nb * P.n_blocks, grid, smem);
 #define ZS_CASE(C, K) if (COUT == C && KC == K) return zs_launch<C, K>(P, smem, grid, stream);

@@ -3,9 +3,12 @@
 #include "b3d_internal.h"
 #include <stdarg.h>
 #include <mutex>
+#include <atomic>
 
 static thread_local char g_err[1024] = "";
-long long g_b3d_launches = 0;
+std::atomic<long long> g_b3d_launches{0};   // the Flask app serves threaded (main.py:1059): count atomically
+
+std::atomic<int> g_b3d_ordered_issue{getenv("B3D_ORDERED_ISSUE") ? atoi(getenv("B3D_ORDERED_ISSUE")) : 0};
 
 void b3d_set_error(const char* fmt, ...) {
   va_list ap;
@@ -70,7 +73,9 @@ int b3d_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uin
 extern "C" {
 const char* b3d_last_error_string() { return g_err; }
 int b3d_version() { return 100; }
-long long b3d_launch_count() { return g_b3d_launches; }
+long long b3d_launch_count() { return g_b3d_launches.load(); }
+// 1: bit-reproducible forward / input gradients (single MMA issuer in the z-marching conv kernel); returns the old value
+int b3d_set_ordered_issue(int on) { return g_b3d_ordered_issue.exchange(on ? 1 : 0); }
 // 0 if the current device is sm_100 (B200); negative otherwise — callers must fail loudly, there is no fallback.
 int b3d_check_device() {
   int dev = 0, major = 0, minor = 0;

@@ -459,11 +459,8 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
                      int N, long long V, int F, float eps, void* stream) {
   B3D_REQUIRE(F % 8 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_bwd: F=%d unsupported", F);
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
-  static bool attr = false;
-  if (!attr) {   // 64 KB at F = 1024
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(gate_psi_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * (int)sizeof(float)));
-    attr = true;
-  }
+  static const cudaError_t attr = cudaFuncSetAttribute(gate_psi_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * (int)sizeof(float));   // one-time, thread-safe
+  B3D_CHECK_CUDA(attr);
   gate_psi_bwd_kernel<<<grid, 256, 16 * F * sizeof(float), (cudaStream_t)stream>>>(
       dpsin, psi_raw, st_psi, st_dpsi, gpsi, (const bf16*)g1r, (const bf16*)x1r, st_g, st_x, gam_g, bet_g, gam_x, bet_x, wpsi,
       (bf16*)dz, sums_g, sums_x, dwpsi, dbpsi, V, F, eps); ++g_b3d_launches;

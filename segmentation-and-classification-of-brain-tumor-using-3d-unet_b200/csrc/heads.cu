@@ -5,7 +5,7 @@
 //     applied to the output of final_conv.0                         /root/reference/main.py:129-134,198
 // Logits are produced as fp32 NCDHW (what the reference returns and what the loss reads).  K (classes) is fixed to 4
 // (BraTS labels 0..3, main.py:336 / train_model.py:174); other values are rejected loudly.
-#include "b3d_common.cuh"
+#include "loss_common.cuh"
 #include "b3d_internal.h"
 #include <algorithm>
 
@@ -54,9 +54,10 @@ __global__ void __launch_bounds__(256) ds_head_fwd_kernel(const bf16* __restrict
   }
 }
 
-// backward of the 1x1 head: dl is PLANAR fp32 [N][K][Vs]; dskip[n][v][c] (+)= Σ_k dl_k W[k][c];
+// backward of the 1x1 head: dl is PLANAR fp32 [N][K][Vs] (CL = false) or channel-last float4 [N][Vs] (CL = true, what the
+// fused deep-supervision loss produces); dskip[n][v][c] (+)= Σ_k dl_k W[k][c];
 // dW[k][c] += Σ dl_k skip_c ; db[k] += Σ dl_k   (fp32 atomics into caller-zeroed buffers)
-template <bool ACC>
+template <bool ACC, bool CL>
 __global__ void __launch_bounds__(256, 3) ds_head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x,
                                                           long long ldx, const float* __restrict__ w, bf16* __restrict__ dx,
                                                           long long lddx, float* __restrict__ dW, float* __restrict__ db,
@@ -87,8 +88,13 @@ __global__ void __launch_bounds__(256, 3) ds_head_bwd_kernel(const float* __rest
     if (v >= NV) continue;
     const long long n = v / Vs, vs = v - n * Vs;
     float g[KCLS];
+    if (CL) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(dl) + v);
+      g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < KCLS; ++k) g[k] = __ldg(dl + (n * KCLS + k) * Vs + vs);
+      for (int k = 0; k < KCLS; ++k) g[k] = __ldg(dl + (n * KCLS + k) * Vs + vs);
+    }
     if (lc == 0) {
 #pragma unroll
       for (int k = 0; k < KCLS; ++k) gb[k] += g[k];
@@ -136,15 +142,6 @@ __global__ void __launch_bounds__(256, 3) ds_head_bwd_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // trilinear upsample (align_corners=False) of low-res logits float4[N][Dl][Hl][Wl] to planar fp32 [N][K][D][H][W]
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void lerp_src(int o, float scale, int nin, int& i0, int& i1, float& l1) {
-  float src = scale * (o + 0.5f) - 0.5f;
-  if (src < 0.f) src = 0.f;
-  i0 = (int)src;
-  if (i0 > nin - 1) i0 = nin - 1;
-  i1 = i0 + ((i0 < nin - 1) ? 1 : 0);
-  l1 = src - (float)i0;
-}
-
 __global__ void __launch_bounds__(256) trilinear_up_fwd_kernel(const float4* __restrict__ lo, float* __restrict__ out, int N,
                                                                int Dl, int Hl, int Wl, int D, int H, int W) {
   const long long V = (long long)D * H * W;
@@ -395,16 +392,32 @@ int b3d_ds_head_fwd(const void* x, long long ldx, const float* w, const float* b
   return B3D_OK;
 }
 
-int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
-                    int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream) {
+static int ds_head_bwd_launch(const float* dl, bool channel_last, const void* x, long long ldx, const float* w, void* dx,
+                              long long lddx, int accumulate, float* dW, float* db, int N, long long Vs, int C, int K,
+                              void* stream) {
   B3D_REQUIRE(K == KCLS, "ds_head: only %d output classes supported (got %d)", KCLS, K);
   B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
   const size_t smem = (2 * KCLS * C + KCLS) * sizeof(float);
   const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 6);
-  if (accumulate) { ds_head_bwd_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C); ++g_b3d_launches; }
-  else { ds_head_bwd_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C); ++g_b3d_launches; }
+  cudaStream_t st = (cudaStream_t)stream;
+#define DSB(A, L) ds_head_bwd_kernel<A, L><<<blocks, 256, smem, st>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C)
+  if (accumulate) { if (channel_last) DSB(true, true); else DSB(true, false); }
+  else { if (channel_last) DSB(false, true); else DSB(false, false); }
+#undef DSB
+  ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
+}
+
+int b3d_ds_head_bwd(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
+                    int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream) {
+  return ds_head_bwd_launch(dl, false, x, ldx, w, dx, lddx, accumulate, dW, db, N, Vs, C, K, stream);
+}
+
+// same, with the logit gradient channel-last: dl float [N][Vs][4] (16-byte aligned)
+int b3d_ds_head_bwd_cl(const float* dl, const void* x, long long ldx, const float* w, void* dx, long long lddx,
+                       int accumulate, float* dW, float* db, int N, long long Vs, int C, int K, void* stream) {
+  return ds_head_bwd_launch(dl, true, x, ldx, w, dx, lddx, accumulate, dW, db, N, Vs, C, K, stream);
 }
 
 int b3d_trilinear_up_fwd(const float* lo, float* out, int N, int Dl, int Hl, int Wl, int D, int H, int W, int K,

@@ -9,28 +9,14 @@
 // All of it is HBM-bound: per output tensor the forward reads logits+targets once (softmax, all reductions), the
 // boundary term is a 7-point stencil pass over the stored softmax, and the backward is one more pass writing dlogits
 // (math: SURVEY App. A7).  No host synchronisation: every scalar stays in a device accumulator until the caller reads it.
-#include "b3d_common.cuh"
+#include "loss_common.cuh"
 #include "b3d_internal.h"
 #include <algorithm>
-
-#define KC 4
-#define ACC_STRIDE 16  // per sample: I[4] P[4] T[4] Σce Σfocal ΣE² pad
-
-struct LossCfg {
-  float w_dice, smooth, w_focal, f_alpha, f_gamma, w_ce, w_boundary, w_tv, tv_alpha, tv_beta, tv_smooth;
-};
 
 static int ls_blocks(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)b3d_num_sms() * 8;
   return (int)std::max<long long>(1, std::min(b, cap));
-}
-
-__device__ __forceinline__ float focal_pow(float base, float gamma) {
-  if (gamma == 2.f) return base * base;
-  if (gamma == 1.f) return base;
-  if (gamma == 0.f) return 1.f;
-  return powf(fmaxf(base, 0.f), gamma);
 }
 
 // pass 1: p = softmax(logits) stored planar; acc[n] += I,P,T,Σce,Σfocal
@@ -293,7 +279,6 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 
 
 // backward, 4 voxels (consecutive x) per thread: the 7-point boundary stencil is served by 128-bit loads (W % 4 == 0)
-__device__ __forceinline__ float sgnf(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
 
 __global__ void __launch_bounds__(256) loss_bwd_vec4_kernel(const float* __restrict__ prob, const float* __restrict__ E,
                                                             const long long* __restrict__ target, const double* __restrict__ acc,
@@ -461,6 +446,11 @@ __global__ void __launch_bounds__(256) voxel_count_kernel(const unsigned char* _
     if (i < KC) atomicAdd(&cls[i], (unsigned long long)s_cnt[i]);
     else atomicAdd(&slices[i - KC], (unsigned long long)s_cnt[i]);
   }
+}
+
+int b3d_launch_loss_finalize(const double* acc, int N, long long V, const LossCfg& cfg, float* values, cudaStream_t st) {
+  loss_finalize_kernel<<<1, 32, 0, st>>>(acc, N, V, cfg, values); ++g_b3d_launches;
+  return B3D_OK;
 }
 
 extern "C" {

@@ -526,12 +526,12 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
   const int per_sample = std::max(1, std::min(ew_blocks(V * (C / 8), GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
   dim3 grid(per_sample, N);
   const size_t smem = 8 * (size_t)C * sizeof(float);   // 4C floats + 2C doubles
-  static bool attr = false;
-  if (!attr) {   // up to 64 KB at C = GN_MAXC (the wide model's 2048-channel concat buffers)
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float)));
-    B3D_CHECK_CUDA(cudaFuncSetAttribute(gn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float)));
-    attr = true;
-  }
+  static const cudaError_t attr = [] {   // one-time, thread-safe; up to 64 KB at C = GN_MAXC (the wide model's 2048-channel concat buffers)
+    cudaError_t e = cudaFuncSetAttribute(gn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+  }();
+  B3D_CHECK_CUDA(attr);
   cudaStream_t st = (cudaStream_t)stream;
   if (relu) { gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }
   else { gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }

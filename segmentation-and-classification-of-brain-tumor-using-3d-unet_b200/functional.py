@@ -243,22 +243,18 @@ def up_gate_bwd(saved, dcat, p, idx):
 # ----------------------------------------------------------------------------------------------------------------
 # deep-supervision head (main.py:137-140,164-171) and final head (main.py:129-134)
 # ----------------------------------------------------------------------------------------------------------------
-def ds_head_fwd(skip, p, i, full_size):
+def ds_head_fwd(skip, p, i):
+    """Low-res logits of deep-supervision head i: fp32 channel-last [N,d,h,w,K].  The trilinear up-sampling to full resolution
+    (main.py:165-170) is NOT done here: the fused loss interpolates in registers, anything else materialises lazily (lazy.py)."""
     k = p["deep_supervision.%d.weight" % i].shape[0]
-    lo = ops.ds_head_fwd(skip, p["deep_supervision.%d.weight" % i].reshape(k, -1), p["deep_supervision.%d.bias" % i])
-    return ops.trilinear_up_fwd(lo, full_size)
+    return ops.ds_head_fwd(skip, p["deep_supervision.%d.weight" % i].reshape(k, -1), p["deep_supervision.%d.bias" % i])
 
 
-def ds_head_bwd(skip, dup, p, i, dskip):
-    """Accumulates into dskip; returns grads."""
-    n, d, h, w, c = skip.shape
+def ds_head_bwd(skip, dlo, p, i, dskip):
+    """dlo: gradient of the LOW-RES logits, fp32 channel-last [N,d,h,w,K].  Accumulates into dskip; returns grads."""
     wgt = p["deep_supervision.%d.weight" % i]
     k = wgt.shape[0]
-    if tuple(dup.shape[2:]) == (d, h, w):
-        dlo = dup.contiguous()
-    else:
-        dlo = ops.trilinear_up_bwd(dup, (d, h, w))
-    dw, db = ops.ds_head_bwd(dlo, skip, wgt.reshape(k, -1), dskip, accumulate=True)
+    dw, db = ops.ds_head_bwd_cl(dlo, skip, wgt.reshape(k, -1), dskip, accumulate=True)
     return {"deep_supervision.%d.weight" % i: dw.reshape(wgt.shape), "deep_supervision.%d.bias" % i: db}
 
 
@@ -311,7 +307,7 @@ def final_bwd(saved, dlogits, p):
 # whole network (main.py:154-203)
 # ----------------------------------------------------------------------------------------------------------------
 def unet_fwd(x_ncdhw, p, bufs, features, training, dropout_masks, need_bwd):
-    """x: fp32 NCDHW.  Returns (main_logits fp32 NCDHW, [deep outputs] (train only), saved)."""
+    """x: fp32 NCDHW.  Returns (main_logits fp32 NCDHW, [low-res deep-supervision logits, channel-last] (train only), saved)."""
     n, cin, d, h, w = x_ncdhw.shape
     if d % 32 or h % 32 or w % 32:
         raise ValueError("UNet3D (b200 path): D,H,W must be multiples of 32, got %s" % ((d, h, w),))
@@ -326,7 +322,7 @@ def unet_fwd(x_ncdhw, p, bufs, features, training, dropout_masks, need_bwd):
         S["enc"].append(sv)
         if training and i < nl - 1:
             with ops.side_branch(ops.BRANCH_MASK & 2, out):
-                deep.append(ds_head_fwd(out, p, i, (d, h, w)))
+                deep.append(ds_head_fwd(out, p, i))
         mask = dropout_masks[i] if (training and dropout_masks is not None) else None
         x = ops.pool_fwd(out, mask)
         S["pool"].append((out, mask))
@@ -346,7 +342,8 @@ def unet_fwd(x_ncdhw, p, bufs, features, training, dropout_masks, need_bwd):
 
 
 def unet_bwd(S, dmain, ddeep, p, features, on_grads=None):
-    """dmain: fp32 NCDHW gradient of the main logits; ddeep: list (entries may be None).  Returns {name: grad}.
+    """dmain: fp32 NCDHW gradient of the main logits; ddeep: gradients of the LOW-RES deep-supervision logits, channel-last
+    (entries may be None).  Returns {name: grad}.
     `on_grads(dict)` is called as soon as a block's parameter gradients exist (reverse-topological order) so a
     data-parallel wrapper can start all-reducing them while the rest of backward runs."""
     nl = len(features)

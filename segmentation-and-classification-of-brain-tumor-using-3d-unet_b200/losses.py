@@ -3,10 +3,13 @@
     CombinedLoss3D / TverskyLoss3D / DeepSupervisionLoss3D      /root/reference/losses.py:7-126
     CombinedLoss / DiceLoss / FocalLoss (trainer-local)          /root/reference/training.py:517-566
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from .lazy import LazyDeepOutput
 
 
 class _LossFn(torch.autograd.Function):
@@ -34,6 +37,27 @@ class _LossFn(torch.autograd.Function):
 
 def _run(pred, target, cfg):
     return _LossFn.apply(pred, target, cfg)
+
+
+class _DsLossFn(torch.autograd.Function):
+    """Fused F.interpolate(trilinear) + loss of one deep-supervision output, straight from its low-res logits (dsloss.cu)."""
+
+    @staticmethod
+    def forward(ctx, lo, tgt_u8, cfg, size):
+        _lib.require_device(lo.device)
+        lod = lo.detach().contiguous()
+        values, acc = ops.dsloss_fwd(lod, tgt_u8, cfg, size)
+        ctx.saved_state, ctx.cfg, ctx.size = (lod, tgt_u8, acc), cfg, size
+        ctx.mark_non_differentiable(values)
+        return values[0].clone(), values
+
+    @staticmethod
+    def backward(ctx, gtotal, _gvalues):
+        lod, tgt_u8, acc = ctx.saved_state
+        g = gtotal.contiguous().float().reshape(1)
+        dlo = ops.dsloss_bwd(lod, tgt_u8, acc, ctx.cfg, g, 1.0, ctx.size)
+        ctx.saved_state = None
+        return dlo, None, None, None
 
 
 class CombinedLoss3D(nn.Module):
@@ -77,6 +101,9 @@ class TverskyLoss3D(nn.Module):
         return _run(pred, target, ops.loss_cfg(w_tv=1.0, tv_alpha=self.alpha, tv_beta=self.beta, tv_smooth=self.smooth))[0]
 
 
+FUSED_DS_LOSS = os.environ.get("B3D_FUSED_DS_LOSS", "1") != "0"   # 0: materialise the up-sampled maps (round-1 path)
+
+
 class DeepSupervisionLoss3D(nn.Module):
     """w0*L(main) + sum_{i<len(w)-1} w_{i+1}*L(deep_i) — losses.py:99-126 (the 4th deep output is unused, as there)."""
 
@@ -85,21 +112,26 @@ class DeepSupervisionLoss3D(nn.Module):
         self.weights = weights
         self.loss_fn = loss_fn or CombinedLoss3D()
 
-    def _one(self, pred, target):
+    def _one(self, pred, target, tgt_u8=None):
+        if isinstance(pred, LazyDeepOutput) and tgt_u8 is not None:   # fused upsample + loss from the low-res head logits
+            return _DsLossFn.apply(pred.lo, tgt_u8, self.loss_fn._cfg(), pred.full_size)[0]
         if hasattr(self.loss_fn, "loss_tensor"):
             return self.loss_fn.loss_tensor(pred, target)
-        return self.loss_fn(pred, target)[0]
+        out = self.loss_fn(pred, target)
+        return out[0] if isinstance(out, tuple) else out
 
     def forward(self, predictions, target):
         if isinstance(predictions, tuple):
             main_pred, deep_preds = predictions
             total = self._one(main_pred, target) * self.weights[0]
-            for i, pred in enumerate(deep_preds):
-                if i < len(self.weights) - 1:
-                    if tuple(pred.shape[2:]) != tuple(target.shape[1:]):
-                        raise ValueError("b200 DeepSupervisionLoss3D: deep outputs must be full resolution (UNet3D "
-                                         "up-samples them, main.py:165-170)")
-                    total = total + self._one(pred, target) * self.weights[i + 1]
+            used = [pred for i, pred in enumerate(deep_preds) if i < len(self.weights) - 1]
+            fused = isinstance(self.loss_fn, CombinedLoss3D) and FUSED_DS_LOSS and any(isinstance(q, LazyDeepOutput) for q in used)
+            tgt_u8 = ops.target_u8(target) if fused else None
+            for i, pred in enumerate(used):
+                if tuple(pred.shape[2:]) != tuple(target.shape[1:]):
+                    raise ValueError("b200 DeepSupervisionLoss3D: deep outputs must be full resolution (UNet3D "
+                                     "up-samples them, main.py:165-170)")
+                total = total + self._one(pred, target, tgt_u8) * self.weights[i + 1]
             return total
         return self._one(predictions, target)
 

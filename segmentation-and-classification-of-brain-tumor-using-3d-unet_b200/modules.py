@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, functional as Fn, ops
+from .lazy import LazyDeepOutput
 
 
 def _conv(cin, cout, k, bias=True):
@@ -226,7 +227,9 @@ class UNet3D(nn.Module):
         names, params = zip(*self.named_parameters())
         outs = _BlockFn.apply(_UNetImpl(self), 1, names, x, *params)
         if self.training and len(outs) > 1:
-            return outs[0], list(outs[1:])
+            # main.py:200-201 returns the up-sampled head maps; here they are lazy views of the low-res head logits (lazy.py)
+            size = tuple(x.shape[2:])
+            return outs[0], [LazyDeepOutput(lo, size) for lo in outs[1:]]
         return outs[0]
 
 

@@ -633,6 +633,19 @@ def ds_head_bwd(dl_planar, x, w, dx, accumulate):
     return dw, db
 
 
+def ds_head_bwd_cl(dl_cl, x, w, dx, accumulate):
+    """As ds_head_bwd, with the logit gradient channel-last: dl_cl fp32 [N,D,H,W,K] (what the fused loss produces)."""
+    n, d, h, wd, c = x.shape
+    k = w.shape[0]
+    dl_cl = dl_cl.contiguous()
+    assert dl_cl.dtype == torch.float32 and tuple(dl_cl.shape) == (n, d, h, wd, k)
+    dw = torch.zeros((k, c), dtype=torch.float32, device=x.device)
+    db = torch.zeros(k, dtype=torch.float32, device=x.device)
+    check(_L().b3d_ds_head_bwd_cl(ptr(dl_cl), ptr(x), c_ll(ld(x)), ptr(w), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
+                                  ptr(dw), ptr(db), c_int(n), c_ll(d * h * wd), c_int(c), c_int(k), stream_ptr()))
+    return dw, db
+
+
 def trilinear_up_fwd(lo, size):
     n, dl, hl, wl, k = lo.shape
     d, h, w = size
@@ -722,6 +735,46 @@ def loss_fwd(logits, target, cfg):
     check(_L().b3d_loss_fwd(ptr(logits), ptr(target), cfg, ptr(prob), ptr(e), ptr(acc), ptr(values), c_int(n), c_int(k),
                             c_int(d), c_int(h), c_int(w), stream_ptr()))
     return values, (prob, e, target, acc)
+
+
+def target_u8(target):
+    """int64 labels [N,D,H,W] -> uint8 (one 33 MB read per loss call instead of one per output and pass)."""
+    n, d, h, w = target.shape
+    target = _check_target(target, (n, d, h, w), target.device, "loss")
+    out = torch.empty((n, d, h, w), dtype=torch.uint8, device=target.device)
+    check(_L().b3d_target_u8(ptr(target), ptr(out), c_ll(target.numel()), stream_ptr()))
+    return out
+
+
+def dsloss_fwd(lo, tgt_u8, cfg, size):
+    """Fused trilinear-upsample + CombinedLoss3D of ONE deep-supervision output from its low-res logits.
+    lo: fp32 [N, D/s, H/s, W/s, 4] channel-last; tgt_u8: uint8 [N, D, H, W]; returns (values[6], acc)."""
+    n, dl, hl, wl, k = lo.shape
+    d, h, w = size
+    s = d // dl
+    if k != 4 or dl * s != d or hl * s != h or wl * s != w or s not in (1, 2, 4, 8):
+        raise _lib.B3DError("dsloss: low-res logits %s do not up-sample to %s by 1/2/4/8" % (tuple(lo.shape), tuple(size)))
+    if tuple(tgt_u8.shape) != (n, d, h, w) or tgt_u8.dtype != torch.uint8:
+        raise _lib.B3DError("dsloss: target must be uint8 [N,D,H,W] = %s" % ((n, d, h, w),))
+    lo = lo.contiguous()
+    acc = torch.empty((n, 16), dtype=torch.float64, device=lo.device)
+    values = torch.empty(6, dtype=torch.float32, device=lo.device)
+    with _prof_bw("dsloss", n * d * h * w * 1 + lo.numel() * 4, "dsloss_fwd s%d" % s):
+        check(_L().b3d_dsloss_fwd(ptr(lo), ptr(tgt_u8), cfg, ptr(acc), ptr(values), c_int(n), c_int(s), c_int(d), c_int(h), c_int(w),
+                                  stream_ptr()))
+    return values, acc
+
+
+def dsloss_bwd(lo, tgt_u8, acc, cfg, gscale, wscale, size):
+    """d(loss)/d(lo) fp32 [N, D/s, H/s, W/s, 4] (accumulated in fp64 for s > 1)."""
+    n, dl, hl, wl, k = lo.shape
+    d, h, w = size
+    s = d // dl
+    out = torch.empty(lo.shape, dtype=torch.float32 if s == 1 else torch.float64, device=lo.device)
+    with _prof_bw("dsloss", n * d * h * w * 1 + lo.numel() * (8 if s == 1 else 12), "dsloss_bwd s%d" % s):
+        check(_L().b3d_dsloss_bwd(ptr(lo), ptr(tgt_u8), ptr(acc), cfg, ptr(gscale), c_float(wscale), ptr(out), c_int(n), c_int(s),
+                                  c_int(d), c_int(h), c_int(w), stream_ptr()))
+    return out if s == 1 else out.float()
 
 
 def loss_bwd(saved, cfg, gscale, wscale, shape):

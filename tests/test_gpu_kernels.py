@@ -246,6 +246,87 @@ def test_loss_fwd_bwd(cfgname):
     assert (dl - gref).abs().max().item() <= 1e-4 * gref.abs().max().item() + 1e-9
 
 
+@pytest.mark.parametrize("scale,size", [(1, (32, 32, 32)), (2, (32, 64, 32)), (4, (64, 32, 32)), (8, (32, 32, 64))])
+def test_fused_deep_supervision_loss_vs_oracle_and_materialised_path(scale, size):
+    """dsloss.cu: trilinear up-sampling (main.py:165-170) + CombinedLoss3D (losses.py:17-75) from LOW-RES logits, forward sums
+    and d/d(low-res logits), against (a) the oracle on the F.interpolate'd map (fp32 CPU) and (b) this library's materialised
+    path (trilinear_up_fwd + loss_fwd/loss_bwd + trilinear_up_bwd), which it must reproduce to fp32 rounding."""
+    from oracle import unet3d_oracle as O
+    n = 2
+    d, h, w = size
+    g = torch.Generator().manual_seed(60 + scale)
+    lo = (torch.randn(n, d // scale, h // scale, w // scale, 4, generator=g) * 2).to(DEV)
+    target = torch.randint(0, 4, (n, d, h, w), generator=g).to(DEV)
+    cfg = ops.loss_cfg(w_dice=0.5, smooth=1e-5, w_focal=0.3, f_alpha=0.25, f_gamma=2.0, w_boundary=0.2)
+    # (a) oracle
+    lt = lo.cpu().clone().requires_grad_(True)
+    up_ref = F.interpolate(lt.permute(0, 4, 1, 2, 3), size=size, mode="trilinear", align_corners=False)
+    ref, parts = O.combined_loss3d(up_ref, target.cpu())
+    (ref * 0.8).backward()
+    # fused
+    t8 = ops.target_u8(target)
+    assert t8.dtype == torch.uint8 and torch.equal(t8.long(), target)
+    values, acc = ops.dsloss_fwd(lo, t8, cfg, size)
+    assert abs(values[0].item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (values.tolist(), ref.item())
+    assert abs(values[1].item() - parts["dice_loss"].item()) < 2e-5
+    assert abs(values[2].item() - parts["focal_loss"].item()) < 2e-5
+    assert abs(values[3].item() - parts["boundary_loss"].item()) < 2e-5
+    gs = torch.full((1,), 0.4, device=DEV)
+    dlo = ops.dsloss_bwd(lo, t8, acc, cfg, gs, 2.0, size)            # 0.4 * 2.0 = 0.8
+    assert dlo.shape == lo.shape and dlo.dtype == torch.float32
+    gref = lt.grad
+    assert (dlo.cpu() - gref).abs().max().item() <= 1e-4 * gref.abs().max().item() + 1e-9
+    # (b) the materialised path of this library
+    up = ops.trilinear_up_fwd(lo, size)
+    v2, saved = ops.loss_fwd(up, target, cfg)
+    assert abs(v2[0].item() - values[0].item()) < 1e-6 * max(1.0, abs(v2[0].item()))
+    dup = ops.loss_bwd(saved, cfg, gs, 2.0, tuple(up.shape))
+    if scale == 1:
+        dlo2 = dup.permute(0, 2, 3, 4, 1)
+    else:
+        dlo2 = ops.trilinear_up_bwd(dup, (d // scale, h // scale, w // scale)).permute(0, 2, 3, 4, 1)
+    assert (dlo - dlo2).abs().max().item() <= 2e-5 * dlo2.abs().max().item() + 1e-10
+    # determinism: fixed-order partials + fp64 atomics
+    v3, acc3 = ops.dsloss_fwd(lo, t8, cfg, size)
+    assert torch.equal(v3, values)
+    dlo3 = ops.dsloss_bwd(lo, t8, acc3, cfg, gs, 2.0, size)
+    assert (dlo3 - dlo).abs().max().item() <= 1e-6 * dlo.abs().max().item()
+
+
+def test_lazy_deep_output_fused_and_materialised_losses_agree():
+    """lazy.LazyDeepOutput: DeepSupervisionLoss3D takes the fused path; the reference-style use (F.softmax / cross_entropy on the
+    tensor itself) materialises it — both give the same value and the same gradient on the low-res logits."""
+    import unet3d_b200 as U
+    from unet3d_b200.lazy import LazyDeepOutput
+    g = torch.Generator().manual_seed(70)
+    size = (32, 32, 32)
+    main = (torch.randn(1, 4, *size, generator=g)).to(DEV).requires_grad_(True)
+    los = [(torch.randn(1, 32 // s, 32 // s, 32 // s, 4, generator=g)).to(DEV).requires_grad_(True) for s in (1, 2, 4, 8)]
+    y = torch.randint(0, 4, (1,) + size, generator=g).to(DEV)
+    crit = U.DeepSupervisionLoss3D()
+    deep = [LazyDeepOutput(lo, size) for lo in los]
+    assert all(tuple(q.shape) == (1, 4) + size and q.dtype == torch.float32 and q.is_cuda for q in deep)
+    la = crit((main, deep), y)
+    assert all(q._full is None for q in deep[:3]), "the fused loss must not materialise the up-sampled maps"
+    la.backward()
+    ga = [lo.grad.clone() for lo in los[:3]]
+    assert los[3].grad is None                                   # 4th deep output unused (losses.py:118-124)
+    for lo in los:
+        lo.grad = None
+    full = [q.materialize() for q in [LazyDeepOutput(lo, size) for lo in los]]
+    assert all(type(f) is torch.Tensor and tuple(f.shape) == (1, 4) + size for f in full)
+    lb = crit((main, full), y)
+    lb.backward()
+    assert abs(float(la) - float(lb)) <= 2e-6 * abs(float(lb))
+    for a, lo in zip(ga, los[:3]):
+        assert (a - lo.grad).abs().max().item() <= 2e-5 * lo.grad.abs().max().item() + 1e-10
+    # reference-style consumers work on the lazy tensor directly
+    q = LazyDeepOutput(los[1], size)
+    ce = F.cross_entropy(q, y)
+    assert abs(float(ce) - float(F.cross_entropy(full[1].detach(), y))) < 1e-6
+    assert torch.equal(q.detach().argmax(1), full[1].argmax(1))
+
+
 def test_confusion_and_voxel_counts_bit_exact():
     from oracle import unet3d_oracle as O
     n, s = 2, 16
