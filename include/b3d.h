@@ -38,6 +38,13 @@ int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void
  * weight [Cin][Cout][8] (main.py:121,130,216,219,229,252,258).  Buffers sized as for b3d_pack_weight. */
 int b3d_pack_weight_pair(int convT, const float* w, int Cout, int Cin, int ntaps, void* out_fprop, void* out_dgrad,
                          void* stream);
+/* One optimizer step of torch.optim.AdamW (training.py:186-191 builds it; training.py:296-304 steps it) for the whole model in
+ * two kernel families: packed conv weights (parameter, both moments AND both bf16 packed copies in one pass — replaces the
+ * re-pack after the step) and everything else.  HOST tables (int64): pack [n][16] = w g m v out_fprop out_dgrad A B T convT
+ * Kp_f rows_f Kp_d rows_d first_tile tiles_b ; flat [n][8] = w g m v numel first_block - - .  lr / step: device floats. */
+int b3d_adamw_step(const long long* pack_table, int n_pack, long long total_tiles, const long long* flat_table, int n_flat,
+                   long long total_blocks, const float* lr, const float* step, float beta1, float beta2, float eps,
+                   float weight_decay, void* stream);
 /* nn.Conv3d(k=3,pad=1) main.py:130,216,219 and nn.Conv3d(k=1) main.py:229,252,258 (forward; with mode-1 weights: the
  * data gradient autograd computes for them).  Optional (+=) GroupNorm/BatchNorm partial sums of the output. */
 int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,

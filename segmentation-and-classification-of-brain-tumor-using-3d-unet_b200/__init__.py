@@ -6,4 +6,4 @@ from .losses import (CombinedLoss3D, TverskyLoss3D, DeepSupervisionLoss3D, Combi
 from .metrics import (calculate_dice_score, dice_score, confusion_matrix, segment, tumor_volumes, classify,  # noqa: F401
                       CLASS_NAMES)
 from .graph import GraphedTrainStep, GraphedInference  # noqa: F401
-from .optim import make_adamw, make_scheduler  # noqa: F401
+from .optim import FusedAdamW, make_adamw, make_scheduler  # noqa: F401

@@ -32,8 +32,30 @@ def _stamp():
     return h.hexdigest()
 
 
+def _obj_stamp(src):
+    """Hash of one translation unit: its source, the headers it includes (transitively, from csrc/ and include/), the flags."""
+    seen, todo = set(), [src]
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    inc_dirs = [CSRC, os.path.join(HERE, "..", "include")]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        data = open(f, "rb").read()
+        h.update(os.path.basename(f).encode())
+        h.update(data)
+        for line in data.decode(errors="ignore").split("\n"):
+            line = line.strip()
+            if line.startswith("#include \""):
+                name = line.split("\"")[1]
+                for d in inc_dirs:
+                    todo.append(os.path.join(d, name))
+    return h.hexdigest()
+
+
 def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into libb3d.so.  Returns the library path."""
+    """Compile the .cu files under csrc/ whose sources / headers changed and link libb3d.so.  Returns the library path."""
     stamp_file = LIB + ".stamp"
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file):
@@ -47,18 +69,27 @@ def build(force=False, verbose=False):
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
+        ostamp = _obj_stamp(src)
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(obj + ".stamp") \
+                and open(obj + ".stamp").read().strip() == ostamp:
+            continue
+        if os.path.exists(obj + ".stamp"):
+            os.remove(obj + ".stamp")
         cmd = [nvcc] + NVCC_FLAGS + ["-I", CSRC, "-I", os.path.join(HERE, "..", "include"), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), obj, ostamp))
     failed = False
-    for src, p in procs:
+    for src, p, obj, ostamp in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             failed = True
             sys.stderr.write("nvcc failed for %s:\n%s\n" % (src, out))
-        elif verbose:
-            sys.stderr.write(out)
+        else:
+            with open(obj + ".stamp", "w") as fh:
+                fh.write(ostamp)
+            if verbose:
+                sys.stderr.write(out)
     if failed:
         raise RuntimeError("libb3d build failed")
     cmd = [nvcc, "-shared", "-o", LIB] + objs

@@ -454,115 +454,6 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Weight packing: reference fp32 layouts -> bf16 [ntaps][rows][Kp]  (K-major rows; one swizzled TMA box per K chunk)
-//   mode 0 conv fprop : W[co][ci][t]          -> k = ci, row = co, tap = t
-//   mode 1 conv dgrad : W[co][ci][t]          -> k = co, row = ci, tap = ntaps-1-t       (flipped + transposed)
-//   (3x3x3: the packed tap index runs (kh,kw,kd) with kd fastest, so the three kd taps of one (kh,kw) are adjacent row
-//    blocks — conv_zs.cu multiplies them in ONE N = 3*Cout MMA)
-//   mode 2 convT fprop: Wt[ci][co][t8]        -> k = ci, row = t8*Cout+co, tap 0
-//   mode 3 convT dgrad: Wt[ci][co][t8]        -> k = t8*Cout+co, row = ci, tap 0
-// ---------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int mode, int Cout, int Cin,
-                                   int ntaps, int Kp, int rows) {
-  const int ptaps = (mode >= 2) ? 1 : ntaps;
-  const long long total = (long long)ptaps * rows * Kp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kp);
-    long long r = i / Kp;
-    const int row = (int)(r % rows);
-    int t = (int)(r / rows);
-    if (ntaps == 27 && mode < 2) t = (t % 3) * 9 + t / 3;  // packed tap order (kh,kw,kd) -> reference order (kd,kh,kw)
-    float val = 0.f;
-    if (mode == 0) {
-      if (k < Cin && row < Cout) val = w[((long long)row * Cin + k) * ntaps + t];
-    } else if (mode == 1) {
-      if (k < Cout && row < Cin) val = w[((long long)k * Cin + row) * ntaps + (ntaps - 1 - t)];
-    } else if (mode == 2) {
-      const int t8 = row / Cout, co = row - t8 * Cout;
-      if (k < Cin && t8 < ntaps) val = w[((long long)k * Cout + co) * ntaps + t8];
-    } else {
-      const int t8 = k / Cout, co = k - t8 * Cout;
-      if (t8 < ntaps && row < Cin) val = w[((long long)row * Cout + co) * ntaps + t8];
-    }
-    out[i] = __float2bfloat16(val);
-  }
-}
-
-// Both packed copies of one weight from ONE coalesced read (a training step re-packs every conv weight after the optimizer
-// moved it: 92 M parameters = 370 MB fp32 in, 2 x 185 MB bf16 out).  A block owns a 16 x 16 tile of the two leading source
-// dimensions with all taps: it reads 16 runs of 16*T contiguous floats into shared memory and writes 32-byte runs (16 bf16
-// along K) into each packed layout.  src[(a*B + b)*T + t]:
-//   conv  (a = co, b = ci): fprop[tp][co][ci]                 dgrad[tp][ci][co] holding tap ntaps-1-t   (tp = packed tap order)
-//   convT (a = ci, b = co): fprop[t8*Cout + co][ci]           dgrad[ci][t8*Cout + co]
-template <bool CONVT>
-__global__ void __launch_bounds__(256) pack_pair_kernel(const float* __restrict__ w, bf16* __restrict__ out_f,
-                                                        bf16* __restrict__ out_d, int A, int B, int T, int Kp_f, int rows_f,
-                                                        int Kp_d, int rows_d) {
-  extern __shared__ float tile[];   // [16 a][16 b][T] (+1 pad per a-row to spread banks)
-  const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
-  const int run = 16 * T, pitch = run + 1;
-  if (b0 + 16 <= B && ((long long)B * T) % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {   // whole, 16-byte aligned runs
-    const int run4 = run / 4;
-    for (int i = threadIdx.x; i < 16 * run4; i += blockDim.x) {
-      const int al = i / run4, r4 = i - al * run4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a0 + al < A) v = __ldg(reinterpret_cast<const float4*>(w + ((long long)(a0 + al) * B + b0) * T) + r4);
-      float* d = tile + al * pitch + 4 * r4;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-  } else {
-    for (int i = threadIdx.x; i < 16 * run; i += blockDim.x) {
-      const int al = i / run, r = i - al * run;
-      const int bl = r / T;
-      float v = 0.f;
-      if (a0 + al < A && b0 + bl < B) v = w[((long long)(a0 + al) * B + b0) * T + r];
-      tile[al * pitch + r] = v;
-    }
-  }
-  __syncthreads();
-  // work item = (tap, line, half): 8 bf16 = 16 bytes; a line is 16 elements along the packed K index
-  const int items = T * 16 * 2;
-  for (int i = threadIdx.x; i < 2 * items; i += blockDim.x) {
-    const bool second = i >= items;            // false: K runs along b (fprop of conv / dgrad of convT); true: K runs along a
-    int j = second ? i - items : i;
-    const int half = j & 1; j >>= 1;
-    const int line = j & 15; const int tp = j >> 4;
-    float v[8];
-    if (!CONVT) {
-      int t = tp;
-      if (T == 27) t = (tp % 3) * 9 + tp / 3;   // packed tap order (kh,kw,kd) -> reference order (kd,kh,kw)
-      if (!second) {   // fprop[tp][co = a0+line][ci = b0 + 8*half ..]
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = tile[line * pitch + (8 * half + e) * T + t];
-        const int co = a0 + line, ci = b0 + 8 * half;
-        if (co < rows_f && ci < Kp_f) stg16(out_f + ((long long)tp * rows_f + co) * Kp_f + ci, pack8(v));
-      } else {         // dgrad[tp][ci = b0+line][co = a0 + 8*half ..], tap flipped
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = tile[(8 * half + e) * pitch + line * T + (T - 1 - t)];
-        const int ci = b0 + line, co = a0 + 8 * half;
-        if (ci < rows_d && co < Kp_d) stg16(out_d + ((long long)tp * rows_d + ci) * Kp_d + co, pack8(v));
-      }
-    } else {
-      const int Cout = B;
-      if (!second) {   // dgrad[ci = a0+line][k = t8*Cout + co .. 8 consecutive co]
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = tile[line * pitch + (8 * half + e) * T + tp];
-        const int ci = a0 + line, co = b0 + 8 * half;
-        if (ci < rows_d && co < Cout) {
-          if (co + 8 <= Cout) stg16(out_d + (long long)ci * Kp_d + (long long)tp * Cout + co, pack8(v));
-          else for (int e = 0; e < 8 && co + e < Cout; ++e) out_d[(long long)ci * Kp_d + (long long)tp * Cout + co + e] = __float2bfloat16(v[e]);
-        }
-      } else {         // fprop[row = t8*Cout + co = b0+line][k = ci = a0 + 8*half ..]
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = tile[(8 * half + e) * pitch + line * T + tp];
-        const int co = b0 + line, ci = a0 + 8 * half;
-        if (co < Cout && ci < Kp_f) stg16(out_f + ((long long)tp * Cout + co) * Kp_f + ci, pack8(v));
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Host side: planner + launcher
 // ---------------------------------------------------------------------------------------------
 static const int kSmemBudget = 227 * 1024 - 2048;
@@ -806,40 +697,6 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
-
-int b3d_pack_weight(int mode, const float* w, int Cout, int Cin, int ntaps, void* out, int Kp, int rows,
-                    void* stream) {
-  B3D_REQUIRE(mode >= 0 && mode <= 3, "pack_weight: bad mode %d", mode);
-  B3D_REQUIRE(Kp % 16 == 0 && rows > 0, "pack_weight: bad Kp/rows");
-  const int ptaps = (mode >= 2) ? 1 : ntaps;
-  const long long total = (long long)ptaps * rows * Kp;
-  int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)out, mode, Cout, Cin, ntaps, Kp, rows); ++g_b3d_launches;
-  B3D_CHECK_CUDA(cudaGetLastError());
-  return B3D_OK;
-}
-
-// Both packed copies of a weight in one launch (modes 0+1 for nn.Conv3d, 2+3 for nn.ConvTranspose3d k2 s2); the layouts
-// are those of b3d_pack_weight.  convT: the dgrad buffer (K = 8*Cout, which need not be a multiple of 16 wide per tap) must be
-// zero-initialised by the caller when 8*Cout < Kp_d (never the case for Cout % 2 == 0).
-int b3d_pack_weight_pair(int convT, const float* w, int Cout, int Cin, int ntaps, void* out_fprop, void* out_dgrad,
-                         void* stream) {
-  B3D_REQUIRE(ntaps >= 1 && ntaps <= 27, "pack_weight_pair: bad ntaps %d", ntaps);
-  const int r16i = (Cin + 15) / 16 * 16, r16o = (Cout + 15) / 16 * 16;
-  const size_t smem = (size_t)16 * (16 * ntaps + 1) * sizeof(float);
-  if (!convT) {
-    dim3 grid(r16i / 16, r16o / 16);   // x: ci tiles (b), y: co tiles (a)
-    pack_pair_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)out_fprop, (bf16*)out_dgrad, Cout, Cin, ntaps,
-                                                                      r16i, r16o, r16o, r16i); ++g_b3d_launches;
-  } else {
-    B3D_REQUIRE(ntaps == 8 && Cout % 8 == 0, "pack_weight_pair: ConvTranspose3d needs 8 taps and Cout %% 8 == 0");
-    dim3 grid((Cout + 15) / 16, r16i / 16);   // x: co tiles (b), y: ci tiles (a)
-    pack_pair_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)out_fprop, (bf16*)out_dgrad, Cin, Cout, 8, r16i,
-                                                                     8 * Cout, 8 * Cout, r16i); ++g_b3d_launches;
-  }
-  B3D_CHECK_CUDA(cudaGetLastError());
-  return B3D_OK;
-}
 
 // Stride-1 "same" convolution, ks in {1,3}.  x: NDHWC bf16 with voxel pitch ldx (elements), Cin channels used (mult of 16).
 // wpack: packed [Cin/8][ks^3][rows][8] (rows = roundup16(Cout)).  y: NDHWC bf16 pitch ldy.  stats: optional double

@@ -46,6 +46,47 @@ __device__ __forceinline__ float4 logit_at(const float4* __restrict__ lo, int Dl
 #undef MIX
 }
 
+// Low-res sub-tile staging (S > 1): the 8 taps of every interpolated point come from shared memory instead of 8 dependent
+// L2 round trips per point.  A tile of T full-res positions plus halo touches at most T/S + 3 low-res cells per axis.
+template <int S> struct LoTile {
+  static constexpr int CZ = TZ / S + 3, CY = TY / S + 3, CX = TX / S + 3, N = (S > 1) ? CZ * CY * CX : 1;
+};
+
+template <int S>
+__device__ __forceinline__ void stage_lo(float4* __restrict__ slo, const float4* __restrict__ lon, int Dl, int Hl, int Wl, int zmin,
+                                         int ymin, int xmin, int& bz, int& by, int& bx) {
+  using LT = LoTile<S>;
+  const float sc = 1.f / (float)S;
+  int i1; float l1;
+  lerp_src(zmin, sc, Dl, bz, i1, l1); lerp_src(ymin, sc, Hl, by, i1, l1); lerp_src(xmin, sc, Wl, bx, i1, l1);
+  for (int i = threadIdx.x; i < LT::N; i += NTHREADS) {
+    const int cx = i % LT::CX, cy = (i / LT::CX) % LT::CY, cz = i / (LT::CX * LT::CY);
+    const int gz = min(bz + cz, Dl - 1), gy = min(by + cy, Hl - 1), gx = min(bx + cx, Wl - 1);
+    slo[i] = ld_lo(lon + ((long long)gz * Hl + gy) * Wl + gx);
+  }
+}
+
+// logit_at<S> served from the staged sub-tile (same arithmetic, term for term)
+template <int S>
+__device__ __forceinline__ float4 logit_tile(const float4* __restrict__ slo, int bz, int by, int bx, int Dl, int Hl, int Wl, int z,
+                                             int y, int x) {
+  using LT = LoTile<S>;
+  const float sc = 1.f / (float)S;
+  int z0, z1, y0, y1, x0, x1; float lz, ly, lx;
+  lerp_src(z, sc, Dl, z0, z1, lz); lerp_src(y, sc, Hl, y0, y1, ly); lerp_src(x, sc, Wl, x0, x1, lx);
+  z0 -= bz; z1 -= bz; y0 -= by; y1 -= by; x0 -= bx; x1 -= bx;
+#define AT(zz, yy, xx) slo[((zz) * LT::CY + (yy)) * LT::CX + (xx)]
+  const float4 v000 = AT(z0, y0, x0), v001 = AT(z0, y0, x1), v010 = AT(z0, y1, x0), v011 = AT(z0, y1, x1);
+  const float4 v100 = AT(z1, y0, x0), v101 = AT(z1, y0, x1), v110 = AT(z1, y1, x0), v111 = AT(z1, y1, x1);
+#undef AT
+  const float wz0 = 1.f - lz, wy0 = 1.f - ly, wx0 = 1.f - lx;
+#define MIX(f)                                                                                         \
+  (wz0 * (wy0 * (wx0 * v000.f + lx * v001.f) + ly * (wx0 * v010.f + lx * v011.f)) +                    \
+   lz * (wy0 * (wx0 * v100.f + lx * v101.f) + ly * (wx0 * v110.f + lx * v111.f)))
+  return make_float4(MIX(x), MIX(y), MIX(z), MIX(w));
+#undef MIX
+}
+
 // softmax of 4 logits exactly as loss_softmax_kernel computes it; also returns ce = lse - z_t and the focal term for class t
 __device__ __forceinline__ float4 softmax4(const float4 zz, int t, float& ce) {
   const float z[KC] = {zz.x, zz.y, zz.z, zz.w};
@@ -78,8 +119,10 @@ template <int S>
 __global__ void __launch_bounds__(NTHREADS) dsloss_fwd_kernel(const float4* __restrict__ lo, const unsigned char* __restrict__ tgt,
                                                               double* __restrict__ acc, int N, int D, int H, int W, LossCfg cfg) {
   constexpr int PZ = TZ + 1, PY = TY + 1, PX = TX + 1, NP = PZ * PY * PX;
-  __shared__ float4 sp[NP];
-  __shared__ unsigned char st[NP];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sp = reinterpret_cast<float4*>(smem_raw);          // [NP] softmax tile
+  float4* slo = sp + NP;                                      // [LoTile<S>::N] staged low-res logits
+  unsigned char* st = reinterpret_cast<unsigned char*>(slo + LoTile<S>::N);   // [NP] labels
   __shared__ double s_acc[15];
   const int Dl = D / S, Hl = H / S, Wl = W / S;
   const int tiles_x = W / TX, tiles_y = H / TY, tiles_z = D / TZ;
@@ -119,6 +162,9 @@ __global__ void __launch_bounds__(NTHREADS) dsloss_fwd_kernel(const float4* __re
     const float4* lon = lo + (long long)n * Dl * Hl * Wl;
     const unsigned char* tn = tgt + (long long)n * V;
     __syncthreads();   // the previous tile's stencil reads are done
+    int bz = 0, by = 0, bx = 0;
+    if (S > 1) { stage_lo<S>(slo, lon, Dl, Hl, Wl, z0, y0, x0, bz, by, bx); __syncthreads(); }
+#pragma unroll 2
     for (int i = threadIdx.x; i < NP; i += NTHREADS) {
       const int dx = i % PX, dy = (i / PX) % PY, dz = i / (PX * PY);
       const int gz = z0 + dz, gy = y0 + dy, gx = x0 + dx;
@@ -127,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS) dsloss_fwd_kernel(const float4* __re
       if (gz < D && gy < H && gx < W) {
         t = tn[((long long)gz * H + gy) * W + gx];
         float ce;
-        p = softmax4(logit_at<S>(lon, Dl, Hl, Wl, gz, gy, gx), t, ce);
+        p = softmax4(S > 1 ? logit_tile<S>(slo, bz, by, bx, Dl, Hl, Wl, gz, gy, gx) : logit_at<S>(lon, Dl, Hl, Wl, gz, gy, gx), t, ce);
         if (dz < TZ && dy < TY && dx < TX) {   // interior point: the per-voxel sums
           a[4] += p.x; a[5] += p.y; a[6] += p.z; a[7] += p.w;
           if (t < KC) {
@@ -228,7 +274,12 @@ __global__ void __launch_bounds__(NTHREADS) dsloss_bwd_kernel(const float4* __re
     const int z0 = (int)(r / tiles_y) * TZ;
     const float4* lon = lo + (long long)n * Dl * Hl * Wl;
     const unsigned char* tn = tgt + (long long)n * V;
-    // ---- softmax tile with halo -1 .. +1 (index 0 <-> global coordinate origin - 1)
+    // ---- softmax tile with halo -1 .. +1 (index 0 <-> global coordinate origin - 1); the staged low-res tile aliases sE
+    int bz = 0, by = 0, bx = 0;
+    float4* slo = sE;
+    static_assert(LoTile<S>::N <= NE, "staged low-res tile must fit the E tile");
+    if (S > 1) { stage_lo<S>(slo, lon, Dl, Hl, Wl, max(z0 - 1, 0), max(y0 - 1, 0), max(x0 - 1, 0), bz, by, bx); __syncthreads(); }
+#pragma unroll 2
     for (int i = threadIdx.x; i < NP; i += NTHREADS) {
       const int dx = i % PX, dy = (i / PX) % PY, dz = i / (PX * PY);
       const int gz = z0 + dz - 1, gy = y0 + dy - 1, gx = x0 + dx - 1;
@@ -237,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS) dsloss_bwd_kernel(const float4* __re
       if (gz >= 0 && gy >= 0 && gx >= 0 && gz < D && gy < H && gx < W) {
         t = tn[((long long)gz * H + gy) * W + gx];
         float ce;
-        p = softmax4(logit_at<S>(lon, Dl, Hl, Wl, gz, gy, gx), t, ce);
+        p = softmax4(S > 1 ? logit_tile<S>(slo, bz, by, bx, Dl, Hl, Wl, gz, gy, gx) : logit_at<S>(lon, Dl, Hl, Wl, gz, gy, gx), t, ce);
       }
       sp[i] = p;
       st[i] = (unsigned char)t;
@@ -427,9 +478,13 @@ __global__ void __launch_bounds__(NTHREADS) dsloss_bwd_kernel(const float4* __re
 template <int S>
 static int launch_fwd(const float4* lo, const unsigned char* tgt, double* acc, int N, int D, int H, int W, const LossCfg& cfg,
                       cudaStream_t st) {
+  constexpr int NP = (TZ + 1) * (TY + 1) * (TX + 1);
+  constexpr size_t smem = (size_t)(NP + LoTile<S>::N) * sizeof(float4) + NP;
+  static const cudaError_t attr = cudaFuncSetAttribute(dsloss_fwd_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (attr != cudaSuccess) { b3d_set_error("dsloss_fwd: cannot raise the shared-memory limit: %s", cudaGetErrorString(attr)); return B3D_ERR_CUDA; }
   const long long ntiles = (long long)N * (D / TZ) * (H / TY) * (W / TX);
-  const int blocks = (int)std::min<long long>(ntiles, (long long)b3d_num_sms() * 4);
-  dsloss_fwd_kernel<S><<<blocks, NTHREADS, 0, st>>>(lo, tgt, acc, N, D, H, W, cfg); ++g_b3d_launches;
+  const int blocks = (int)std::min<long long>(ntiles, (long long)b3d_num_sms() * 3);
+  dsloss_fwd_kernel<S><<<blocks, NTHREADS, smem, st>>>(lo, tgt, acc, N, D, H, W, cfg); ++g_b3d_launches;
   return B3D_OK;
 }
 
@@ -469,13 +524,15 @@ int b3d_dsloss_fwd(const float* lo, const unsigned char* target_u8, const float*
   cudaStream_t st = (cudaStream_t)stream;
   B3D_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * ACC_STRIDE * N, st));
   const float4* l4 = (const float4*)lo;
+  int rc = B3D_OK;
   switch (scale) {
-    case 1: launch_fwd<1>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
-    case 2: launch_fwd<2>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
-    case 4: launch_fwd<4>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
-    case 8: launch_fwd<8>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
+    case 1: rc = launch_fwd<1>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
+    case 2: rc = launch_fwd<2>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
+    case 4: rc = launch_fwd<4>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
+    case 8: rc = launch_fwd<8>(l4, target_u8, acc, N, D, H, W, cfg, st); break;
     default: b3d_set_error("dsloss: scale %d unsupported (1,2,4,8)", scale); return B3D_ERR_UNSUPPORTED;
   }
+  if (rc != B3D_OK) return rc;
   b3d_launch_loss_finalize(acc, N, (long long)D * H * W, cfg, values, st);
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;

@@ -89,28 +89,32 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // squeeze-excite: ca[n][c] = sigmoid(b2[c] + Σ_j W2[c][j] * relu(b1[j] + Σ_k W1[j][k] * mean[n][k]))
 // ------------------------------------------------------------------------------------------------
-__global__ void gate_se_fwd_kernel(const double* __restrict__ xsum, long long V, const float* __restrict__ w1,
+__global__ void __launch_bounds__(256) gate_se_fwd_kernel(const double* __restrict__ xsum, long long V, const float* __restrict__ w1,
                                    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                    float* __restrict__ ca, float* __restrict__ zbuf, float* __restrict__ meanbuf, int C) {
+  // one CTA per sample; every mat-vec row is owned by a WARP (lanes stride the contiguous row, shuffle reduction), so the
+  // weight reads are coalesced and all 8 warps work (the first version let C/8 threads walk rows with stride-C loads)
   extern __shared__ float sm[];
   float* mean = sm; float* z = sm + C;
   const int n = blockIdx.x, R = C / 8;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     mean[c] = (float)(xsum[(long long)n * C + c] / (double)V);
     meanbuf[(long long)n * C + c] = mean[c];
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < R; j += blockDim.x) {
-    float a = b1[j];
-    for (int k = 0; k < C; ++k) a = fmaf(w1[(long long)j * C + k], mean[k], a);
-    z[j] = fmaxf(a, 0.f);
-    zbuf[(long long)n * R + j] = z[j];
+  for (int j = wrp; j < R; j += nw) {
+    float a = 0.f;
+    for (int k = lane; k < C; k += 32) a = fmaf(__ldg(w1 + (long long)j * C + k), mean[k], a);
+    a = warp_sum(a);
+    if (lane == 0) { const float v = fmaxf(a + b1[j], 0.f); z[j] = v; zbuf[(long long)n * R + j] = v; }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = b2[c];
-    for (int j = 0; j < R; ++j) a = fmaf(w2[(long long)c * R + j], z[j], a);
-    ca[(long long)n * C + c] = 1.f / (1.f + __expf(-a));
+  for (int c = wrp; c < C; c += nw) {
+    float a = 0.f;
+    for (int j = lane; j < R; j += 32) a = fmaf(__ldg(w2 + (long long)c * R + j), z[j], a);
+    a = warp_sum(a);
+    if (lane == 0) ca[(long long)n * C + c] = 1.f / (1.f + __expf(-(a + b2[c])));
   }
 }
 
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
 
 // SE backward (one block per sample).  Param grads are accumulated with fp32 atomics into caller-zeroed buffers.
 // xadd[n][c] = d(mean_c)/V : the constant the SE branch adds to every voxel of dx.
-__global__ void gate_se_bwd_kernel(const double* __restrict__ dca, const float* __restrict__ ca, const float* __restrict__ zbuf,
+__global__ void __launch_bounds__(256) gate_se_bwd_kernel(const double* __restrict__ dca, const float* __restrict__ ca, const float* __restrict__ zbuf,
                                    const float* __restrict__ meanbuf, const float* __restrict__ w1, const float* __restrict__ w2,
                                    long long V, float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                                    float* __restrict__ db2, float* __restrict__ xadd, int C) {
@@ -233,6 +237,7 @@ __global__ void gate_se_bwd_kernel(const double* __restrict__ dca, const float* 
   const int R = C / 8;
   float* dp2 = sm; float* dp1 = sm + C; float* z = sm + C + R; float* mean = sm + C + 2 * R;
   const int n = blockIdx.x;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float cc = ca[(long long)n * C + c];
     dp2[c] = (float)dca[(long long)n * C + c] * cc * (1.f - cc);
@@ -245,11 +250,24 @@ __global__ void gate_se_bwd_kernel(const double* __restrict__ dca, const float* 
     const int c = i / R, j = i - c * R;
     atomicAdd(&dW2[i], dp2[c] * z[j]);
   }
-  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+  // dp1[j] = Σ_c W2[c][j] dp2[c]: warps split the rows c, lanes the (contiguous) columns j; the per-warp partials are summed
+  // in FIXED order (this feeds an input gradient: no order-dependent atomics)
+  float* part = mean + C;   // [nw][R]
+  for (int j0 = 0; j0 < R; j0 += 32) {
+    const int j = j0 + lane;
     float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(w2[(long long)c * R + j], dp2[c], a);
-    dp1[j] = z[j] > 0.f ? a : 0.f;
-    atomicAdd(&db1[j], dp1[j]);
+    if (j < R) {
+      for (int c = wrp; c < C; c += nw) a = fmaf(__ldg(w2 + (long long)c * R + j), dp2[c], a);
+      part[wrp * R + j] = a;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    float acc = 0.f;
+    for (int w = 0; w < nw; ++w) acc += part[w * R + j];
+    const float v = z[j] > 0.f ? acc : 0.f;
+    dp1[j] = v;
+    atomicAdd(&db1[j], v);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
@@ -258,7 +276,7 @@ __global__ void gate_se_bwd_kernel(const double* __restrict__ dca, const float* 
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f;
-    for (int j = 0; j < R; ++j) a = fmaf(w1[(long long)j * C + c], dp1[j], a);
+    for (int j = 0; j < R; ++j) a = fmaf(__ldg(w1 + (long long)j * C + c), dp1[j], a);
     xadd[(long long)n * C + c] = a / (float)V;
   }
 }
@@ -446,7 +464,7 @@ int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long lon
 int b3d_gate_se_bwd(const double* dca, const float* ca, const float* zbuf, const float* meanbuf, const float* w1,
                     const float* w2, long long V, float* dW1, float* db1, float* dW2, float* db2, float* xadd, int N, int C,
                     void* stream) {
-  gate_se_bwd_kernel<<<N, 256, (2 * C + 2 * (C / 8)) * sizeof(float), (cudaStream_t)stream>>>(dca, ca, zbuf, meanbuf, w1, w2, V, dW1,
+  gate_se_bwd_kernel<<<N, 256, (2 * C + 10 * (C / 8)) * sizeof(float), (cudaStream_t)stream>>>(dca, ca, zbuf, meanbuf, w1, w2, V, dW1,
                                                                                              db1, dW2, db2, xadd, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;

@@ -19,6 +19,11 @@ def packed(param, mode):
     `clear_pack_cache()`.  (A global cache keyed by id(param) is wrong: a new model can reuse the id, the version and —
     through the caching allocator — even the address of a freed parameter.)
     Both copies a layer needs (fprop + dgrad) are produced by one launch from one read of the fp32 weight."""
+    pin = param.__dict__.get("_b3d_pack_pinned")
+    if pin is not None:   # optim.FusedAdamW wrote these copies in the same pass that updated the parameter
+        if pin[0] == param._version and pin[1] == param.data_ptr():
+            return pin[2][mode]
+        del param.__dict__["_b3d_pack_pinned"]   # the parameter was changed behind the optimizer (load_state_dict, .to, ...)
     cache = param.__dict__.setdefault("_b3d_pack", {})
     key = (param._version, param.data_ptr(), _PACK_EPOCH[0])
     hit = cache.get(mode)

@@ -112,9 +112,11 @@ def test_ordered_issue_mode_is_bit_reproducible_at_128():
     x, y = O.make_inputs(1, 128, 128, 128, seed=35)
     model = _model(feats, sd)
     xd = x.to(DEV)
+    model.eval()
+    with torch.no_grad():
+        c = model(xd).clone()          # default mode (two ping-pong issuers)
     prev = _lib.set_ordered_issue(True)
     try:
-        model.eval()
         with torch.no_grad():
             a, b = model(xd).clone(), model(xd).clone()
         assert torch.equal(a, b), "eval forward differs between two runs in ordered-issue mode"
@@ -130,9 +132,6 @@ def test_ordered_issue_mode_is_bit_reproducible_at_128():
         assert rel_l2(outs[0][2], outs[1][2]) <= 1e-5      # weight gradients: fp32 atomics in the flush (leaves)
     finally:
         _lib.set_ordered_issue(prev)
-    model.eval()
-    with torch.no_grad():
-        c = model(xd)
     assert rel_l2(c.cpu(), a.cpu()) <= 2.5e-2
 
 

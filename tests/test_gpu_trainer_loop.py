@@ -203,6 +203,99 @@ def test_scheduler_changes_the_update_under_graph_replay():
     step.close()
 
 
+def test_fused_adamw_matches_torch_adamw_and_keeps_packed_weights_current():
+    """optim.FusedAdamW: 5 steps with the trainer's hyper-parameters (training.py:186-191) against
+    torch.optim.AdamW on identical gradients — parameters and both moments agree to fp32 rounding; the bf16 packed copies the
+    kernel wrote in the same pass are BIT-identical to a fresh pack of the updated parameter; a scheduler moves the lr; the
+    state_dict is torch.optim.AdamW-compatible (loads into torch's optimizer and back)."""
+    from unet3d_b200 import ops
+    sd = O.make_state_dict(4, 4, FEATS, seed=48)
+    ma, mb = _model(sd), _model(sd)
+    lr0 = 3e-3
+    oa = U.FusedAdamW(ma, lr=torch.tensor(lr0, device=DEV), weight_decay=1e-4, betas=(0.9, 0.999))
+    ob = torch.optim.AdamW(mb.parameters(), lr=lr0, weight_decay=1e-4, betas=(0.9, 0.999))
+    sa, sb = U.make_scheduler(oa, T_0=3, T_mult=1, eta_min=1e-6), U.make_scheduler(ob, T_0=3, T_mult=1, eta_min=1e-6)
+    g = torch.Generator().manual_seed(5)
+    skip = {"deep_supervision.3.weight", "deep_supervision.3.bias"}      # never receive a gradient (losses.py:118-124)
+    for step in range(5):
+        for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            if k in skip:
+                pa.grad = pb.grad = None
+                continue
+            gr = (torch.randn(pa.shape, generator=g) * (0.1 + 0.05 * step)).to(DEV)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step(); sa.step(); sb.step()
+        assert abs(float(oa.param_groups[0]["lr"]) - ob.param_groups[0]["lr"]) < 1e-9
+    packed = U.optim.packed_conv_params(ma)
+    assert len(packed) == 49        # 11 blocks x 3 convs + 5 gates x 2 + 5 transposed convs + final_conv.0
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        if k in skip:
+            assert torch.equal(pa, pb) and pa not in oa.state
+            continue
+        scale = float(pb.abs().max()) + 1e-12
+        assert float((pa - pb).abs().max()) <= 2e-5 * scale + 1e-7, k
+        for key in ("exp_avg", "exp_avg_sq"):
+            ref = ob.state[pb][key]
+            assert float((oa.state[pa][key] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-12, (k, key)
+        if id(pa) in packed:
+            convt = packed[id(pa)][1]
+            fresh = ops.pack_weight_pair(pa, convt)
+            pin = pa.__dict__["_b3d_pack_pinned"][2]
+            for mode, (buf, kp, rows) in fresh.items():
+                assert pin[mode][1:] == (kp, rows)
+                assert torch.equal(pin[mode][0], buf), "packed copy of %s (mode %d) is stale" % (k, mode)
+    assert float(oa.state[next(iter(oa.state))]["step"]) == 5.0
+    # the pinned copies are what the conv kernels use; a parameter changed behind the optimizer drops the pin
+    from unet3d_b200 import functional
+    w = ma.downs[0].double_conv[0].weight
+    assert functional.packed(w, ops.PACK_FPROP)[0] is w.__dict__["_b3d_pack_pinned"][2][ops.PACK_FPROP][0]
+    with torch.no_grad():
+        w.mul_(2.0)
+    got = functional.packed(w, ops.PACK_FPROP)[0]
+    assert "_b3d_pack_pinned" not in w.__dict__ and torch.equal(got, ops.pack_weight_pair(w, False)[ops.PACK_FPROP][0])
+    # checkpoint compatibility (training.py:398-404 saves optimizer.state_dict())
+    sd_a = oa.state_dict()
+    oc = torch.optim.AdamW(ma.parameters(), lr=lr0, weight_decay=1e-4)
+    oc.load_state_dict(sd_a)
+    od = U.FusedAdamW(ma, lr=torch.tensor(lr0, device=DEV), weight_decay=1e-4)
+    od.load_state_dict(ob.state_dict())
+    assert float(od._step_t) == 5.0
+
+
+def test_fused_adamw_training_trajectory_follows_the_oracle():
+    """Five steps of the real loop with FusedAdamW (eager): the loss trajectory follows the fp32 CPU oracle + torch.optim.AdamW."""
+    sd = O.make_state_dict(4, 4, FEATS, seed=13)
+    x, y = O.make_inputs(2, 32, 32, 32, seed=13)
+    steps, lr = 5, 2e-3
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    osd = {k: v.clone() for k, v in sd.items()}
+    osd.update(params)
+    oopt = torch.optim.AdamW(list(params.values()), lr=lr, weight_decay=1e-4)
+    ref = []
+    for _ in range(steps):
+        oopt.zero_grad()
+        main, deep, _ = O.unet_forward(x, osd, FEATS, training=True, dropout_masks=None)
+        loss = O.deep_supervision_loss(main, deep, y)
+        loss.backward()
+        oopt.step()
+        ref.append(float(loss.detach()))
+    model = _model(sd).train()
+    crit = U.DeepSupervisionLoss3D()
+    opt = U.make_adamw(model, lr=lr, weight_decay=1e-4)
+    assert isinstance(opt, U.FusedAdamW)
+    xd, yd = x.to(DEV), y.to(DEV)
+    got = []
+    for _ in range(steps):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(xd), yd)
+        loss.backward()
+        opt.step()
+        got.append(float(loss.detach()))
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert abs(a - b) <= 1.5e-2 * abs(a), "step %d: oracle %s vs b200 %s" % (i, ref, got)
+    assert (ref[0] - got[-1]) >= 0.7 * (ref[0] - ref[-1]), "b200 path trains slower than the oracle: %s vs %s" % (got, ref)
+
+
 def test_loss_and_metric_reject_non_int64_targets():
     logits = torch.randn(1, 4, 8, 8, 8, device=DEV)
     for bad in (torch.zeros(1, 8, 8, 8, dtype=torch.uint8, device=DEV), torch.zeros(1, 8, 8, 8, dtype=torch.int32, device=DEV),
