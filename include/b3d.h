@@ -43,8 +43,8 @@ int b3d_pack_weight_pair(int convT, const float* w, int Cout, int Cin, int ntaps
  * re-pack after the step) and everything else.  HOST tables (int64): pack [n][16] = w g m v out_fprop out_dgrad A B T convT
  * Kp_f rows_f Kp_d rows_d first_tile tiles_b ; flat [n][8] = w g m v numel first_block - - .  lr / step: device floats. */
 int b3d_adamw_step(const long long* pack_table, int n_pack, long long total_tiles, const long long* flat_table, int n_flat,
-                   long long total_blocks, const float* lr, const float* step, float beta1, float beta2, float eps,
-                   float weight_decay, void* stream);
+                   long long total_blocks, const float* lr, const float* step, double beta1, double beta2, double eps,
+                   double weight_decay, void* stream);
 /* nn.Conv3d(k=3,pad=1) main.py:130,216,219 and nn.Conv3d(k=1) main.py:229,252,258 (forward; with mode-1 weights: the
  * data gradient autograd computes for them).  Optional (+=) GroupNorm/BatchNorm partial sums of the output. */
 int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
@@ -56,6 +56,11 @@ int b3d_conv_fprop_add(const void* x, long long ldx, const void* wpack, int w_ro
                        long long ld_add, void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int ks,
                        double* stats, int groups, int stats_batch, void* ws, size_t ws_bytes, int* err_flag, void* stream);
 /* nn.ConvTranspose3d(2f,f,k=2,s=2) main.py:121,183 forward / data gradient */
+/* y = conv1x1(x) + addend with the addend carried on K through an identity block of the weights ([W ; I]): the fused
+ * gradient accumulation of main.py:240 (residual branch) and main.py:297 (gate branches) in backward.  wpack_aug: bf16
+ * [Cout][Cin + Cout] = [mode-1 packed W | identity]; y may alias addend. */
+int b3d_conv1_add_mma(const void* x, long long ldx, const void* addend, long long ld_add, const void* wpack_aug, int w_rows,
+                      void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);
 int b3d_convT2_fprop(const void* x, long long ldx, const void* wpack, const float* bias, void* y, long long ldy, int N,
                      int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);
 int b3d_convT2_dgrad(const void* dy, long long lddy, const void* wpack, int w_rows, void* dx, long long lddx, int N, int D,

@@ -744,6 +744,38 @@ int b3d_conv_fprop_add(const void* x, long long ldx, const void* wpack, int w_ro
                    groups, stats_batch, (float*)ws, ws_bytes, err_flag, (cudaStream_t)stream, (const bf16*)addend, ld_add);
 }
 
+// y = conv1x1(x) + addend with the ADDEND ON THE TENSOR CORE: K = [x channels | addend channels], B = [W ; I].  The addend
+// tile arrives through the same TMA pipeline as x (prefetched `stages` tiles ahead) instead of 64-byte per-thread loads in
+// the epilogue, whose DRAM latency the 4 epilogue warps cannot hide (profiles/ncu_r1_igemm_pw_add_16_32.txt: 42 % of the stall
+// samples).  bf16 addend x 1.0 accumulated in fp32 = exactly the epilogue add.  wpack_aug: bf16 [rows][Cin + Cout] =
+// [dgrad-packed W | identity]; y may alias addend (in-place gradient accumulation: every tile reads only rows it later writes).
+int b3d_conv1_add_mma(const void* x, long long ldx, const void* addend, long long ld_add, const void* wpack_aug, int w_rows,
+                      void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream) {
+  B3D_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && w_rows == Cout, "conv1_add_mma: Cin/Cout must be multiples of 16");
+  B3D_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ld_add % 8 == 0, "conv1_add_mma: pitches must be multiples of 8 elements");
+  int a = Cin, b = Cout;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int cpm = a;                       // channels per K-map = gcd(Cin, Cout)
+  const int nx = Cin / cpm, na = Cout / cpm;
+  B3D_REQUIRE(cpm % 16 == 0 && nx + na <= 8, "conv1_add_mma: %d + %d channels need more than 8 K-maps", Cin, Cout);
+  long long V = (long long)N * D * H * W;   // pointwise: flatten all voxels to a [rows][256] plane so tiles are dense
+  int ww = 256;
+  while (ww > 1 && V % ww) ww /= 2;
+  long long hh = V / ww;
+  int dd = 1;
+  while (hh > 32768 && hh % 2 == 0) { hh /= 2; dd *= 2; }
+  ActView v[8];
+  for (int m = 0; m < nx + na; ++m) {
+    const bool isx = m < nx;
+    const long long ld = isx ? ldx : ld_add;
+    v[m].base = (const char*)(isx ? x : addend) + (long long)(isx ? m : m - nx) * cpm * 2;
+    v[m].C = cpm; v[m].W = ww; v[m].H = (int)hh; v[m].D = dd; v[m].N = 1;
+    v[m].sW = ld * 2; v[m].sH = v[m].sW * ww; v[m].sD = v[m].sH * hh; v[m].sN = v[m].sD * dd;
+  }
+  return run_igemm(v, nx + na, cpm, (const bf16*)wpack_aug, w_rows, 1, 1, dd, (int)hh, ww, Cout, 0, (bf16*)y, ldy, 0, nullptr,
+                   nullptr, 0, 0, 0, nullptr, 0, err_flag, (cudaStream_t)stream);
+}
+
 int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
                    int N, int D, int H, int W, int Cin, int Cout, int ks, double* stats, int groups, int stats_batch,
                    void* ws, size_t ws_bytes, int* err_flag, void* stream) {

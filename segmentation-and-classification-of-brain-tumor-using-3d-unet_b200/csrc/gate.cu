@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // squeeze-excite: ca[n][c] = sigmoid(b2[c] + Σ_j W2[c][j] * relu(b1[j] + Σ_k W1[j][k] * mean[n][k]))
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gate_se_fwd_kernel(const double* __restrict__ xsum, long long V, const float* __restrict__ w1,
+__global__ void __launch_bounds__(512) gate_se_fwd_kernel(const double* __restrict__ xsum, long long V, const float* __restrict__ w1,
                                    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                    float* __restrict__ ca, float* __restrict__ zbuf, float* __restrict__ meanbuf, int C) {
   // one CTA per sample; every mat-vec row is owned by a WARP (lanes stride the contiguous row, shuffle reduction), so the
@@ -103,18 +103,32 @@ __global__ void __launch_bounds__(256) gate_se_fwd_kernel(const double* __restri
     meanbuf[(long long)n * C + c] = mean[c];
   }
   __syncthreads();
-  for (int j = wrp; j < R; j += nw) {
-    float a = 0.f;
-    for (int k = lane; k < C; k += 32) a = fmaf(__ldg(w1 + (long long)j * C + k), mean[k], a);
-    a = warp_sum(a);
-    if (lane == 0) { const float v = fmaxf(a + b1[j], 0.f); z[j] = v; zbuf[(long long)n * R + j] = v; }
+  // four rows per warp pass, all loads of the pass in flight before the first use: the kernel is pure DRAM latency
+  // (one CTA per sample streams 2 x C*C/8 floats), so memory-level parallelism is the only thing that matters
+  for (int j0 = wrp * 4; j0 < R; j0 += nw * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < C; k += 32) {
+      float wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wv[i] = (j0 + i < R) ? __ldg(w1 + (long long)(j0 + i) * C + k) : 0.f;
+      const float mk = mean[k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = fmaf(wv[i], mk, a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float s = warp_sum(a[i]);
+      if (lane == 0 && j0 + i < R) { const float v = fmaxf(s + b1[j0 + i], 0.f); z[j0 + i] = v; zbuf[(long long)n * R + j0 + i] = v; }
+    }
   }
   __syncthreads();
-  for (int c = wrp; c < C; c += nw) {
+  // second mat-vec: one THREAD per output channel, its row of W2 (R contiguous floats) read with independent loads
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* wr = w2 + (long long)c * R;
     float a = 0.f;
-    for (int j = lane; j < R; j += 32) a = fmaf(__ldg(w2 + (long long)c * R + j), z[j], a);
-    a = warp_sum(a);
-    if (lane == 0) ca[(long long)n * C + c] = 1.f / (1.f + __expf(-(a + b2[c])));
+#pragma unroll 8
+    for (int j = 0; j < R; ++j) a = fmaf(__ldg(wr + j), z[j], a);
+    ca[(long long)n * C + c] = 1.f / (1.f + __expf(-(a + b2[c])));
   }
 }
 
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
 
 // SE backward (one block per sample).  Param grads are accumulated with fp32 atomics into caller-zeroed buffers.
 // xadd[n][c] = d(mean_c)/V : the constant the SE branch adds to every voxel of dx.
-__global__ void __launch_bounds__(256) gate_se_bwd_kernel(const double* __restrict__ dca, const float* __restrict__ ca, const float* __restrict__ zbuf,
+__global__ void __launch_bounds__(512) gate_se_bwd_kernel(const double* __restrict__ dca, const float* __restrict__ ca, const float* __restrict__ zbuf,
                                    const float* __restrict__ meanbuf, const float* __restrict__ w1, const float* __restrict__ w2,
                                    long long V, float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                                    float* __restrict__ db2, float* __restrict__ xadd, int C) {
@@ -257,6 +271,7 @@ __global__ void __launch_bounds__(256) gate_se_bwd_kernel(const double* __restri
     const int j = j0 + lane;
     float a = 0.f;
     if (j < R) {
+#pragma unroll 8
       for (int c = wrp; c < C; c += nw) a = fmaf(__ldg(w2 + (long long)c * R + j), dp2[c], a);
       part[wrp * R + j] = a;
     }
@@ -276,6 +291,7 @@ __global__ void __launch_bounds__(256) gate_se_bwd_kernel(const double* __restri
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f;
+#pragma unroll 8
     for (int j = 0; j < R; ++j) a = fmaf(__ldg(w1 + (long long)j * C + c), dp1[j], a);
     xadd[(long long)n * C + c] = a / (float)V;
   }
@@ -433,7 +449,7 @@ int b3d_gate_psi_fwd(const void* g1r, const void* x1r, const double* st_g, const
 int b3d_gate_se_fwd(const double* xsum, long long V, const float* w1, const float* b1, const float* w2, const float* b2,
                     float* ca, float* zbuf, float* meanbuf, int N, int C, void* stream) {
   B3D_REQUIRE(C % 8 == 0 && C <= 4096, "gate_se_fwd: bad C");
-  gate_se_fwd_kernel<<<N, 256, (C + C / 8) * sizeof(float), (cudaStream_t)stream>>>(xsum, V, w1, b1, w2, b2, ca, zbuf, meanbuf, C); ++g_b3d_launches;
+  gate_se_fwd_kernel<<<N, 512, (C + C / 8) * sizeof(float), (cudaStream_t)stream>>>(xsum, V, w1, b1, w2, b2, ca, zbuf, meanbuf, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -464,7 +480,7 @@ int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long lon
 int b3d_gate_se_bwd(const double* dca, const float* ca, const float* zbuf, const float* meanbuf, const float* w1,
                     const float* w2, long long V, float* dW1, float* db1, float* dW2, float* db2, float* xadd, int N, int C,
                     void* stream) {
-  gate_se_bwd_kernel<<<N, 256, (2 * C + 10 * (C / 8)) * sizeof(float), (cudaStream_t)stream>>>(dca, ca, zbuf, meanbuf, w1, w2, V, dW1,
+  gate_se_bwd_kernel<<<N, 512, (2 * C + 18 * (C / 8)) * sizeof(float), (cudaStream_t)stream>>>(dca, ca, zbuf, meanbuf, w1, w2, V, dW1,
                                                                                              db1, dW2, db2, xadd, C); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;

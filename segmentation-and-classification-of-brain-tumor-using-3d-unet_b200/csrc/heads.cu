@@ -34,6 +34,39 @@ __global__ void __launch_bounds__(256) ds_head_fwd_kernel(const bf16* __restrict
   const int lc = lane % lanes_c, lv = lane / lanes_c;
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  if (C8 <= 32) {
+    // few channels (levels 0-2: the launches that move hundreds of MB): every lane owns ONE 16-byte chunk per voxel, so four
+    // voxel groups are loaded back to back before the first FMA — 4 independent loads in flight per lane instead of 1
+    constexpr int UF = 4;
+    float wk[KCLS][8];
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wk[k][j] = (lc < C8) ? sw[k * C + lc * 8 + j] : 0.f;
+    for (long long v0 = warp_id * vpw * UF; v0 < NV; v0 += nwarps * vpw * UF) {
+      uint4 raw[UF];
+#pragma unroll
+      for (int u = 0; u < UF; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        raw[u] = (v < NV && lc < C8) ? ldg16_stream(x + v * ldx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UF; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        float a[8], acc[KCLS] = {0.f, 0.f, 0.f, 0.f};
+        unpack8(raw[u], a);
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(a[j], wk[k][j], acc[k]);
+        for (int o = lanes_c >> 1; o > 0; o >>= 1)
+#pragma unroll
+          for (int k = 0; k < KCLS; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lc == 0 && v < NV) out[v] = make_float4(acc[0] + b[0], acc[1] + b[1], acc[2] + b[2], acc[3] + b[3]);
+      }
+    }
+    return;
+  }
   for (long long v0 = warp_id * vpw; v0 < NV; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     float acc[KCLS] = {0.f, 0.f, 0.f, 0.f};
@@ -58,7 +91,7 @@ __global__ void __launch_bounds__(256) ds_head_fwd_kernel(const bf16* __restrict
 // fused deep-supervision loss produces); dskip[n][v][c] (+)= Σ_k dl_k W[k][c];
 // dW[k][c] += Σ dl_k skip_c ; db[k] += Σ dl_k   (fp32 atomics into caller-zeroed buffers)
 template <bool ACC, bool CL>
-__global__ void __launch_bounds__(256, 3) ds_head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) ds_head_bwd_kernel(const float* __restrict__ dl, const bf16* __restrict__ x,
                                                           long long ldx, const float* __restrict__ w, bf16* __restrict__ dx,
                                                           long long lddx, float* __restrict__ dW, float* __restrict__ db,
                                                           int N, long long Vs, int C) {
@@ -83,6 +116,53 @@ __global__ void __launch_bounds__(256, 3) ds_head_bwd_kernel(const float* __rest
 #pragma unroll
     for (int j = 0; j < 8; ++j) gw[k][j] = 0.f;
   float gb[KCLS] = {0.f, 0.f, 0.f, 0.f};
+  if (nchunks == 1 && CL) {
+    // every lane owns one 16-byte chunk per voxel: two voxel groups per iteration, all their loads (logit gradient, skip,
+    // running dskip) issued before the first FMA
+    constexpr int UB = 2;
+    float wk[KCLS][8];
+#pragma unroll
+    for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wk[k][j] = (lc < C8) ? sw[k * C + lc * 8 + j] : 0.f;
+    for (long long v0 = warp_id * vpw * UB; v0 < NV; v0 += nwarps * vpw * UB) {
+      uint4 xa[UB], xo[UB];
+      float4 g4[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        const bool ok = v < NV && lc < C8;
+        g4[u] = ok ? __ldg(reinterpret_cast<const float4*>(dl) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xa[u] = ok ? ldg16_stream(x + v * ldx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        if (ACC) xo[u] = ok ? ldg16(dx + v * lddx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        if (!(v < NV && lc < C8)) continue;
+        const float g[KCLS] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+        if (lc == 0) {
+#pragma unroll
+          for (int k = 0; k < KCLS; ++k) gb[k] += g[k];
+        }
+        float a[8], o[8];
+        unpack8(xa[u], a);
+        if (ACC) unpack8(xo[u], o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int k = 0; k < KCLS; ++k) sacc = fmaf(g[k], wk[k][j], sacc);
+          o[j] = ACC ? o[j] + sacc : sacc;
+        }
+        stg16(dx + v * lddx + lc * 8, pack8(o));
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gw[k][j] = fmaf(g[k], a[j], gw[k][j]);
+      }
+    }
+  } else
   for (long long v0 = warp_id * vpw; v0 < NV; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     if (v >= NV) continue;

@@ -55,30 +55,39 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
 // ---------------------------------------------------------------------------------------------------------------------
 // AdamW (decoupled weight decay), the arithmetic of torch's fused kernel in fp32
 // ---------------------------------------------------------------------------------------------------------------------
+// The scalar constants are formed in DOUBLE exactly as torch does on the host (1 - beta, lr * wd, bias corrections, lr / bc1)
+// and rounded to fp32 once; the per-element arithmetic uses IEEE division / square root (the library is built with
+// --use_fast_math, whose approximate forms would cost 2 ulp per step against torch.optim.AdamW).
 struct AdamConsts {
   float lr_wd;        // lr * weight_decay
-  float beta1, beta2;
+  float beta2, omb1, omb2;   // beta2, 1 - beta1, 1 - beta2
   float step_size;    // lr / (1 - beta1^t)
-  float inv_bc2_sqrt; // 1 / sqrt(1 - beta2^t)
+  float bc2_sqrt;     // sqrt(1 - beta2^t)
   float eps;
 };
 
-__device__ __forceinline__ AdamConsts adam_consts(const float* __restrict__ lr_p, const float* __restrict__ step_p, float beta1,
-                                                  float beta2, float eps, float wd) {
-  const float lr = *lr_p, t = *step_p;
-  AdamConsts c;
-  c.lr_wd = lr * wd; c.beta1 = beta1; c.beta2 = beta2; c.eps = eps;
-  c.step_size = lr / (1.f - powf(beta1, t));
-  c.inv_bc2_sqrt = rsqrtf(1.f - powf(beta2, t));
-  return c;
+__device__ __forceinline__ AdamConsts adam_consts(const float* __restrict__ lr_p, const float* __restrict__ step_p, double beta1,
+                                                  double beta2, double eps, double wd) {
+  __shared__ AdamConsts s_c;
+  if (threadIdx.x == 0) {
+    const double lr = (double)*lr_p, t = (double)*step_p;
+    AdamConsts c;
+    c.lr_wd = (float)(lr * wd); c.beta2 = (float)beta2; c.omb1 = (float)(1.0 - beta1); c.omb2 = (float)(1.0 - beta2);
+    c.eps = (float)eps;
+    c.step_size = (float)(lr / (1.0 - pow(beta1, t)));
+    c.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, t));
+    s_c = c;
+  }
+  __syncthreads();
+  return s_c;
 }
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamConsts& c) {
-  p -= c.lr_wd * p;
-  m = m + (1.f - c.beta1) * (g - m);                 // lerp(m, g, 1 - beta1)
-  v = c.beta2 * v + (1.f - c.beta2) * g * g;
-  const float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
-  p -= c.step_size * m / denom;
+  p = __fsub_rn(p, __fmul_rn(c.lr_wd, p));                        // param.mul_(1 - lr * wd)  (same value to 1 ulp)
+  m = __fmaf_rn(c.omb1, __fsub_rn(g, m), m);                       // exp_avg.lerp_(grad, 1 - beta1)
+  v = __fmaf_rn(__fmul_rn(c.omb2, g), g, __fmul_rn(c.beta2, v));   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
+  p = __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(m, denom)));   // param.addcdiv_(exp_avg, denom, value = -step_size)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -203,7 +212,7 @@ struct FlatTab { long long r[ADAM_MAXF][8]; };
 
 __global__ void __launch_bounds__(256) adamw_pack_multi_kernel(const __grid_constant__ PackTab T_, int ntensors, long long tile_base,
                                                                const float* __restrict__ lr_p, const float* __restrict__ step_p,
-                                                               float beta1, float beta2, float eps, float wd) {
+                                                               double beta1, double beta2, double eps, double wd) {
   extern __shared__ float tile[];
   const long long bid = tile_base + blockIdx.x;
   int lo = 0, hi = ntensors - 1;            // last tensor whose first tile <= bid
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(256) adamw_pack_multi_kernel(const __grid_cons
 
 __global__ void __launch_bounds__(256) adamw_flat_multi_kernel(const __grid_constant__ FlatTab T_, int ntensors, long long block_base,
                                                                const float* __restrict__ lr_p, const float* __restrict__ step_p,
-                                                               float beta1, float beta2, float eps, float wd) {
+                                                               double beta1, double beta2, double eps, double wd) {
   const long long bid = block_base + blockIdx.x;
   int lo = 0, hi = ntensors - 1;
   while (lo < hi) {
@@ -289,8 +298,8 @@ int b3d_pack_weight_pair(int convT, const float* w, int Cout, int Cin, int ntaps
 // The tables are copied into kernel parameters (chunks of 64 / 256 tensors per launch).  lr, step: device floats (step already
 // incremented for this update).
 int b3d_adamw_step(const long long* pack_table, int n_pack, long long total_tiles, const long long* flat_table, int n_flat,
-                   long long total_blocks, const float* lr, const float* step, float beta1, float beta2, float eps,
-                   float weight_decay, void* stream) {
+                   long long total_blocks, const float* lr, const float* step, double beta1, double beta2, double eps,
+                   double weight_decay, void* stream) {
   B3D_REQUIRE(total_tiles < (1ll << 31) && total_blocks < (1ll << 31), "adamw_step: too many tiles");
   cudaStream_t st = (cudaStream_t)stream;
   for (int first = 0; first < n_pack; first += ADAM_MAXP) {

@@ -69,6 +69,13 @@ def act_padded(n, d, h, w, c, device):
     return full[..., :c], full
 
 
+GRAD_SINK = None   # data parallel: callable(name, shape) -> fp32 tensor the weight-gradient kernel writes into (or None)
+
+
+def _sink(name, shape):
+    return GRAD_SINK(name, tuple(shape)) if GRAD_SINK is not None else None
+
+
 def bias_grad(dy):
     """Σ over all voxels and samples -> fp32 [C]."""
     return ops.channel_sum(dy).sum(dim=0).float()
@@ -122,13 +129,13 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
                     dout, r, st_r, p[pre + "residual.1.weight"], p[pre + "residual.1.bias"], 8, False)
         dy2, grads[pre + "double_conv.4.weight"], grads[pre + "double_conv.4.bias"] = ops.gn_bwd(
             dout, y2, st2, p[pre + "double_conv.4.weight"], p[pre + "double_conv.4.bias"], 8, True)
-    grads[pre + "double_conv.3.weight"] = ops.conv_wgrad(a1, dy2, cout, cout, 3)
+    grads[pre + "double_conv.3.weight"] = ops.conv_wgrad(a1, dy2, cout, cout, 3, dw=_sink(pre + "double_conv.3.weight", w2.shape))
     w2d, _, rows2d = packed(w2, ops.PACK_DGRAD)
     da1, _ = ops.conv_fprop(dy2, w2d, rows2d, cout, 3)
     del dy2
     dy1, grads[pre + "double_conv.1.weight"], grads[pre + "double_conv.1.bias"] = ops.gn_bwd(
         da1, y1, st1, p[pre + "double_conv.1.weight"], p[pre + "double_conv.1.bias"], 8, True, dx=da1)
-    grads[pre + "double_conv.0.weight"] = ops.conv_wgrad(x, dy1, cin_real, cout, 3)
+    grads[pre + "double_conv.0.weight"] = ops.conv_wgrad(x, dy1, cin_real, cout, 3, dw=_sink(pre + "double_conv.0.weight", w1.shape))
     dx = None
     if need_dx:
         w1d, _, rows1d = packed(w1, ops.PACK_DGRAD)
@@ -137,7 +144,8 @@ def double_conv_bwd(saved, dout, p, pre, need_dx=True):
     if r is not None:
         if br is not None:
             br.join()
-        grads[pre + "residual.0.weight"] = ops.conv_wgrad(x, dr, cin_real, cout, 1)
+        grads[pre + "residual.0.weight"] = ops.conv_wgrad(x, dr, cin_real, cout, 1,
+                                                          dw=_sink(pre + "residual.0.weight", p[pre + "residual.0.weight"].shape))
         if need_dx:
             wrd, _, rowsrd = packed(p[pre + "residual.0.weight"], ops.PACK_DGRAD)
             ops.conv_fprop(dr, wrd, rowsrd, x.shape[-1], 1, out=dx, add=dx)   # dx += residual-branch gradient, fused
@@ -204,9 +212,9 @@ def gate_bwd(saved, dout, p, pre, dg_add=None):
     _, grads[pre + "W_x.1.weight"], grads[pre + "W_x.1.bias"] = ops.gn_bwd(
         dz, x1r, st_x, p[pre + "W_x.1.weight"], p[pre + "W_x.1.bias"], 4, False, dx=dx1r, sums=sums_x)
     del dz
-    grads[pre + "W_g.0.weight"] = ops.conv_wgrad(g, dg1r, c, f, 1)
+    grads[pre + "W_g.0.weight"] = ops.conv_wgrad(g, dg1r, c, f, 1, dw=_sink(pre + "W_g.0.weight", p[pre + "W_g.0.weight"].shape))
     grads[pre + "W_g.0.bias"] = bias_grad(dg1r)
-    grads[pre + "W_x.0.weight"] = ops.conv_wgrad(x, dx1r, c, f, 1)
+    grads[pre + "W_x.0.weight"] = ops.conv_wgrad(x, dx1r, c, f, 1, dw=_sink(pre + "W_x.0.weight", p[pre + "W_x.0.weight"].shape))
     grads[pre + "W_x.0.bias"] = bias_grad(dx1r)
     wgd, _, rowsgd = packed(p[pre + "W_g.0.weight"], ops.PACK_DGRAD)
     wxd, _, rowsxd = packed(p[pre + "W_x.0.weight"], ops.PACK_DGRAD)
@@ -238,7 +246,7 @@ def up_gate_bwd(saved, dcat, p, idx):
     x_low, gsaved, cin, c = saved
     du, dskip, grads = gate_bwd(gsaved, dcat[..., :c], p, "ups.%d." % (idx + 1), dg_add=dcat[..., c:])
     wt = p["ups.%d.weight" % idx]
-    grads["ups.%d.weight" % idx] = ops.convT2_wgrad(x_low, du, cin, c)
+    grads["ups.%d.weight" % idx] = ops.convT2_wgrad(x_low, du, cin, c, dw=_sink("ups.%d.weight" % idx, wt.shape))
     grads["ups.%d.bias" % idx] = bias_grad(du)
     wtd, _, rowsd = packed(wt, ops.PACK_CONVT_DGRAD)
     dx_low = ops.convT2_dgrad(du, wtd, rowsd, cin)
@@ -301,7 +309,7 @@ def final_bwd(saved, dlogits, p):
         dh, dh_k = dh_s, dh_full
     else:
         dh_k = dh
-    grads["final_conv.0.weight"] = ops.conv_wgrad(x, dh, c, f2, 3)
+    grads["final_conv.0.weight"] = ops.conv_wgrad(x, dh, c, f2, 3, dw=_sink("final_conv.0.weight", w0.shape))
     grads["final_conv.0.bias"] = bias_grad(dh)
     w0d, _, rows0d = packed(w0, ops.PACK_DGRAD)
     dx, _ = ops.conv_fprop(dh_k, w0d, rows0d, c, 3)

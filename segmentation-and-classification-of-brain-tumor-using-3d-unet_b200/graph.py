@@ -32,6 +32,13 @@ class GraphedTrainStep:
                 group["lr"] = group["lr"].to(example_x.device)
         self.x = example_x.detach().clone()
         self.y = example_y.detach().clone()
+        # input pipelining (prefetch / step_prefetched): staging buffers, copy stream and events exist before the first timed
+        # step — allocating them lazily cost a one-off 100+ ms (allocator growth next to the graph's private pool)
+        self._copy_stream = torch.cuda.Stream()
+        self._sx, self._sy = torch.empty_like(self.x), torch.empty_like(self.y)
+        self._staged = torch.cuda.Event()
+        self._consumed = torch.cuda.Event()
+        self._consumed.record()
         self.graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -77,12 +84,6 @@ class GraphedTrainStep:
     # -- input pipelining: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes ----------
     def prefetch(self, x_host, y_host):
         """Start copying the NEXT batch (pinned host tensors) into staging buffers on a side stream."""
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream()
-            self._sx, self._sy = torch.empty_like(self.x), torch.empty_like(self.y)
-            self._staged = torch.cuda.Event()
-            self._consumed = torch.cuda.Event()
-            self._consumed.record()
         self._copy_stream.wait_event(self._consumed)       # the previous staged batch has been moved into the static buffers
         with torch.cuda.stream(self._copy_stream):
             self._sx.copy_(x_host, non_blocking=True)

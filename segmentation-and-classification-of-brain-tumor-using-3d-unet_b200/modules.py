@@ -173,10 +173,16 @@ class _UNetImpl:
             x, hbuf = saved["final"][0], saved["final"][1]
             k = p["final_conv.3.weight"].shape[0]
             dmain = torch.zeros((x.shape[0], k) + tuple(x.shape[1:4]), dtype=torch.float32, device=x.device)
-        grads = Fn.unet_bwd(saved, dmain, list(gouts[1:]), p, list(self.model.features), on_grads=self.model._on_grads)
+        Fn.GRAD_SINK = self.model._grad_sink   # data parallel: weight-gradient kernels write into the all-reduce buckets
+        try:
+            grads = Fn.unet_bwd(saved, dmain, list(gouts[1:]), p, list(self.model.features), on_grads=self.model._on_grads)
+        finally:
+            Fn.GRAD_SINK = None
         ops.wgrad_join()
         if self.model._on_backward_end is not None:
             self.model._on_backward_end()  # data parallel: join the gradient all-reduces before autograd sees the grads
+        if self.model._grad_views is not None:
+            grads = self.model._grad_views(grads)
         return [None], grads
 
 
@@ -209,6 +215,8 @@ class UNet3D(nn.Module):
         self.apply(self._init_weights)
         self._on_grads = None  # hooks for data-parallel gradient bucketing (parallel.py)
         self._on_backward_end = None
+        self._grad_sink = None
+        self._grad_views = None
         for a, b in zip(features[:-1], features[1:]):
             if b != 2 * a:
                 raise ValueError("UNet3D: features must double at every level (the reference decoder requires it)")

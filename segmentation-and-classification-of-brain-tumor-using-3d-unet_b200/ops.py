@@ -17,6 +17,12 @@ from ._lib import c_int, c_ll, c_sz, c_vp, check, ptr, stream_ptr
 
 c_float, c_double = ctypes.c_float, ctypes.c_double
 EPS = 1e-5
+
+
+def _os_environ_flag(name, default):
+    import os
+    v = os.environ.get(name)
+    return default if v is None else v != "0"
 PROFILE = None  # bench.py sets this to a list: (family, algorithmic flops, start event, end event) per tensor-core call
 
 
@@ -188,6 +194,9 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
     dev = x.device
     if out is None:
         out = new_act(n, d, h, w, cout, dev)
+    if (add is not None and ADD_ON_MMA and ks == 1 and bias is None and not groups and cin % 16 == 0 and cout % 16 == 0
+            and w_rows == cout and _gcd_maps(cin, cout) <= 8):
+        return _conv1_add_mma(x, wpack, w_rows, cin, cout, add, out), None
     stats = None
     if groups:
         stats = zeros_scratch((1 if stats_batch else n, groups, 2), torch.float64, dev)
@@ -202,6 +211,33 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
                                   c_int(groups), c_int(1 if stats_batch else 0), ptr(ws),
                                   c_sz(ws_bytes if ws is not None else 0), ptr(_lib.err_flag(dev)), stream_ptr()))
     return out, stats
+
+
+ADD_ON_MMA = _os_environ_flag("B3D_ADD_ON_MMA", True)
+_EYE = {}
+
+
+def _gcd_maps(cin, cout):
+    import math
+    g = math.gcd(cin, cout)
+    return (cin + cout) // g if g % 16 == 0 else 99
+
+
+def _conv1_add_mma(x, wpack, w_rows, cin, cout, add, out):
+    """out = conv1x1(x) + add with the addend riding the tensor core's K dimension: B = [W ; I] (see b3d_conv1_add_mma)."""
+    n, d, h, w, _ = x.shape
+    dev = x.device
+    eye = _EYE.get((cout, dev))
+    if eye is None:
+        eye = _EYE[(cout, dev)] = torch.eye(cout, dtype=torch.bfloat16, device=dev)
+    aug = torch.cat([wpack.view(w_rows, cin), eye], dim=1)          # [Cout][Cin + Cout]: a few KB .. 1.5 MB per layer
+    nbytes = n * d * h * w * (cin + 2 * cout) * 2
+    with _prof("igemm", 2.0 * n * d * h * w * cin * cout, "conv1 %dx%dx%dx%d %d->%d +add" % (n, d, h, w, cin, cout)), \
+            _prof_bw("pointwise_add", nbytes, "conv1+add"):
+        check(_L().b3d_conv1_add_mma(ptr(x), c_ll(ld(x)), ptr(add), c_ll(ld(add)), ptr(aug), c_int(w_rows), ptr(out), c_ll(ld(out)),
+                                     c_int(n), c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(_lib.err_flag(dev)),
+                                     stream_ptr()))
+    return out
 
 
 def convT2_fprop(x, wpack, bias, cout, out=None):

@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import _lib, ops
 from ._lib import c_int, c_ll, check, ptr, stream_ptr
 
-c_float = ctypes.c_float
+c_double = ctypes.c_double
 FLAT_CHUNK = 4096   # elements per CTA of the flat kernel (ADAM_FLAT_CHUNK in pack.cu)
 
 
@@ -173,8 +173,8 @@ class FusedAdamW(torch.optim.Optimizer):
             host_p, host_f, n_pack, tiles, n_flat, blocks = cached[1]
             beta1, beta2 = group["betas"]
             check(_lib.lib().b3d_adamw_step(ptr(host_p), c_int(n_pack), c_ll(tiles), ptr(host_f), c_int(n_flat),
-                                            c_ll(blocks), ptr(self._lr_tensor(gi, group)), ptr(self._step_t), c_float(beta1),
-                                            c_float(beta2), c_float(group["eps"]), c_float(group["weight_decay"]), stream_ptr()))
+                                            c_ll(blocks), ptr(self._lr_tensor(gi, group)), ptr(self._step_t), c_double(beta1),
+                                            c_double(beta2), c_double(group["eps"]), c_double(group["weight_decay"]), stream_ptr()))
             for p in plist:   # the packed copies written by the kernel ARE the current ones: functional.packed returns them
                 st = self.state[p]
                 if "_b3d_bufs" in st:
