@@ -36,6 +36,7 @@ class GradientBuckets:
         self._flat = []           # bucket tensors
         self._remaining = []      # per bucket: gradients still missing in this pass
         self._count = []          # per bucket: gradients per pass
+        self._views_valid = False
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -167,6 +168,7 @@ class GradientBuckets:
         """Flush what is left, wait for every all-reduce; first pass: scatter the averaged values back and fix the layout."""
         if self.world() == 1:
             return
+        self._views_valid = self._layout is not None   # this pass's gradients live in the buckets (not so in the first pass)
         if self._layout is not None:
             for b, rem in enumerate(self._remaining):   # a bucket whose gradients did not all arrive this pass
                 if rem >= 0 and rem < self._count[b]:
@@ -197,7 +199,7 @@ class GradientBuckets:
     def fresh_views(self, grads):
         """Replace bucket-resident gradients by NEW view objects (autograd adopts a gradient it holds the only reference to
         without copying; `.grad` then aliases the bucket)."""
-        if self._layout is None or self.world() == 1:
+        if self._layout is None or self.world() == 1 or not self._views_valid:
             return grads
         return {k: (self.view(k) if (v is not None and k in self._layout) else v) for k, v in grads.items()}
 

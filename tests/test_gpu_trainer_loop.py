@@ -314,4 +314,5 @@ def test_data_parallel_gradients_equal_mean_of_local_gradients_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29731", os.path.join(ROOT, "scripts", "dp_check.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2500:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
