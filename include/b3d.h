@@ -171,6 +171,20 @@ int b3d_confusion(const float* logits, const long long* target, unsigned char* m
 int b3d_voxel_counts(const unsigned char* mask, long long V, int W, unsigned long long* cls, unsigned long long* slices,
                      void* stream);
 
+/* ---- input pipeline in front of the path (preprocess.cu): BraTSDataset._preprocess_image training.py:117-132,
+ *      _preprocess_segmentation training.py:134-146, _apply_augmentations training.py:148-172 ----------------------------- */
+/* exact np.percentile(x, (q_lo, q_hi)) by radix select + mean / population std of the clipped values; stats <- double[4]
+ * {p_lo, p_hi, mean, std}; work: >= 4*2048*4 + 64 bytes of device scratch */
+int b3d_clip_stats(const float* x, long long n, double q_lo, double q_hi, void* work, size_t work_bytes, double* stats,
+                   void* stream);
+/* out = ndimage.zoom(order=1)( (clip(x) - mean) / (std + 1e-8) ) as float32 [OD][OH][OW] */
+int b3d_zoom_normalize(const float* x, int D, int H, int W, const double* stats, float* out, int OD, int OH, int OW, void* stream);
+/* label 4 -> 3 and ndimage.zoom(order=0); out_dtype 0 = uint8, 1 = int64 */
+int b3d_zoom_labels(const float* seg, int D, int H, int W, void* out, int out_dtype, int OD, int OH, int OW, void* stream);
+/* rot90 by k in the (D,H) plane, flips, + N(0, noise_std) (counter RNG), * scale; lab optional (lab_dtype 0 uint8 / 1 int64) */
+int b3d_augment(const float* img, const void* lab, int lab_dtype, float* out_img, void* out_lab, int C, int D, int H, int W, int k,
+                int flip_d, int flip_h, int flip_w, float noise_std, float scale, unsigned long long seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

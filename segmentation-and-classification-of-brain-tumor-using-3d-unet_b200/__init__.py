@@ -7,3 +7,5 @@ from .metrics import (calculate_dice_score, dice_score, confusion_matrix, segmen
                       CLASS_NAMES)
 from .graph import GraphedTrainStep, GraphedInference  # noqa: F401
 from .optim import FusedAdamW, make_adamw, make_scheduler  # noqa: F401
+from . import preprocess  # noqa: F401,E402
+from .preprocess import preprocess_image, preprocess_segmentation, preprocess_case, draw_augmentation, apply_augmentations  # noqa: F401,E402

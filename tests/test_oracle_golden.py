@@ -1,5 +1,7 @@
 """Pins oracle/unet3d_oracle.py against the golden vectors produced by executing the reference's own classes
 (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -141,3 +143,59 @@ def test_classifier_oracle_matches_reference_golden():
         ref = torch.from_numpy(z["logits_" + name])
         assert got.shape == ref.shape
         assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# input pipeline: oracle/preprocess_oracle.py vs the outputs of the reference's own BraTSDataset methods
+# ---------------------------------------------------------------------------------------------------------------------
+def _pp_golden():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "preprocess.json")) as fh:
+        return json.load(fh)
+
+
+def _pp_idx(numel, k=512):
+    g = np.random.RandomState(12345)
+    return np.sort(g.choice(numel, size=min(k, numel), replace=False))
+
+
+def _pp_volume(seed, shape):
+    rng = np.random.RandomState(seed)
+    vol = np.round(rng.gamma(2.0, 300.0, size=shape)).astype(np.float64)
+    vol[rng.rand(*shape) < 0.3] = 0
+    seg = rng.choice([0, 1, 2, 4], size=shape, p=[0.7, 0.1, 0.1, 0.1]).astype(np.float64)
+    return vol, seg
+
+
+def test_preprocess_oracle_matches_reference_golden():
+    from oracle import preprocess_oracle as P
+    g = _pp_golden()
+    for case in g["cases"][:2]:   # the 128^3 identity-size case is covered on the GPU side (keeps the CPU suite short)
+        vol, seg = _pp_volume(case["seed"], tuple(case["shape"]))
+        img, st = P.preprocess_image(vol)
+        lab = P.preprocess_segmentation(seg)
+        for k in ("p1", "p99", "mean", "std"):
+            assert abs(st[k] - case["stats"][k]) <= 1e-9 * max(1.0, abs(case["stats"][k])), k
+        flat = img.astype(np.float64).reshape(-1)
+        np.testing.assert_allclose(flat[_pp_idx(flat.size)], case["image"]["samples"], rtol=0, atol=1e-6)
+        assert abs(flat.sum() - case["image"]["sum"]) <= 1e-3 and abs(np.abs(flat).sum() - case["image"]["abs_sum"]) <= 1e-2
+        assert [int(v) for v in np.bincount(lab.reshape(-1), minlength=4)] == case["label_counts"]
+        assert [int(v) for v in lab.reshape(-1)[_pp_idx(lab.size)]] == case["label_samples"]
+
+
+def test_augmentation_oracle_matches_reference_golden():
+    from oracle import preprocess_oracle as P
+    g = _pp_golden()
+    vol, seg = _pp_volume(3, (30, 36, 28))
+    img, _ = P.preprocess_image(vol)
+    lab = P.preprocess_segmentation(seg)
+    image4 = np.stack([img[:16, :16, :16] * (1 + 0.1 * c) for c in range(4)], 0).astype(np.float64)
+    lab16 = lab[:16, :16, :16].copy()
+    for rec in g["augment"]:
+        np.random.seed(rec["seed"])
+        a, s, prm = P.apply_augmentations(image4.copy(), lab16.copy())
+        assert prm["k"] == rec["params"]["k"] and prm["flips"] == rec["params"]["flips"]
+        assert abs(prm["noise_std"] - rec["params"]["noise_std"]) < 1e-15 and abs(prm["scale"] - rec["params"]["scale"]) < 1e-15
+        flat = a.reshape(-1)
+        np.testing.assert_allclose(flat[_pp_idx(flat.size)], rec["image"]["samples"], rtol=0, atol=1e-12)
+        assert [int(v) for v in s.reshape(-1)[_pp_idx(s.size)]] == rec["label_samples"]
