@@ -614,10 +614,11 @@ def gate_apply_bwd(dout, x, psi_raw, st_psi, gpsi, bpsi_n, ca, dx):
 def gate_se_bwd(dca, ca, z, mean, w1, w2, v):
     n, c = ca.shape
     dev = ca.device
-    dw1 = torch.zeros_like(w1, dtype=torch.float32).reshape(c // 8, c)
-    db1 = torch.zeros(c // 8, dtype=torch.float32, device=dev)
-    dw2 = torch.zeros_like(w2, dtype=torch.float32).reshape(c, c // 8)
-    db2 = torch.zeros(c, dtype=torch.float32, device=dev)
+    # the four small gradient accumulators come out of ONE zero-filled arena slice (no fill kernel each)
+    r = c // 8
+    buf = zeros_scratch((2 * r * c + r + c,), torch.float32, dev)
+    dw1, dw2 = buf[:r * c].view(r, c), buf[r * c:2 * r * c].view(c, r)
+    db1, db2 = buf[2 * r * c:2 * r * c + r], buf[2 * r * c + r:]
     xadd = torch.empty((n, c), dtype=torch.float32, device=dev)
     check(_L().b3d_gate_se_bwd(ptr(dca), ptr(ca), ptr(z), ptr(mean), ptr(w1), ptr(w2), c_ll(v), ptr(dw1), ptr(db1), ptr(dw2),
                                ptr(db2), ptr(xadd), c_int(n), c_int(c), stream_ptr()))
@@ -630,7 +631,7 @@ def gate_psi_bwd(dpsin, psi_raw, st_psi, st_dpsi, gpsi, g1r, x1r, st_g, st_x, ga
     dz = torch.empty_like(g1r)
     sums_g = zeros_scratch((n, f, 2), torch.float64, dev)
     sums_x = zeros_scratch((n, f, 2), torch.float64, dev)
-    small = torch.zeros(f + 3, dtype=torch.float32, device=dev)  # dwpsi[f], dbpsi, dgpsi, dbpsi_n
+    small = zeros_scratch((f + 3,), torch.float32, dev)  # dwpsi[f], dbpsi, dgpsi, dbpsi_n
     check(_L().b3d_gate_psi_bwd(ptr(dpsin), ptr(psi_raw), ptr(st_psi), ptr(st_dpsi), ptr(gpsi), ptr(g1r), ptr(x1r), ptr(st_g),
                                 ptr(st_x), ptr(gam_g), ptr(bet_g), ptr(gam_x), ptr(bet_x), ptr(wpsi), ptr(dz), ptr(sums_g),
                                 ptr(sums_x), c_vp(small.data_ptr()), c_vp(small.data_ptr() + 4 * f),
@@ -662,8 +663,8 @@ def ds_head_bwd(dl_planar, x, w, dx, accumulate):
     """dl_planar fp32 [N,K,D,H,W] (low-res) ; accumulates into dx (bf16 NDHWC) ; returns (dW [K,C], db [K])."""
     n, d, h, wd, c = x.shape
     k = w.shape[0]
-    dw = torch.zeros((k, c), dtype=torch.float32, device=x.device)
-    db = torch.zeros(k, dtype=torch.float32, device=x.device)
+    buf = zeros_scratch((k * c + k,), torch.float32, x.device)
+    dw, db = buf[:k * c].view(k, c), buf[k * c:]
     check(_L().b3d_ds_head_bwd(ptr(dl_planar), ptr(x), c_ll(ld(x)), ptr(w), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
                                ptr(dw), ptr(db), c_int(n), c_ll(d * h * wd), c_int(c), c_int(k), stream_ptr()))
     return dw, db
@@ -675,8 +676,8 @@ def ds_head_bwd_cl(dl_cl, x, w, dx, accumulate):
     k = w.shape[0]
     dl_cl = dl_cl.contiguous()
     assert dl_cl.dtype == torch.float32 and tuple(dl_cl.shape) == (n, d, h, wd, k)
-    dw = torch.zeros((k, c), dtype=torch.float32, device=x.device)
-    db = torch.zeros(k, dtype=torch.float32, device=x.device)
+    buf = zeros_scratch((k * c + k,), torch.float32, x.device)
+    dw, db = buf[:k * c].view(k, c), buf[k * c:]
     check(_L().b3d_ds_head_bwd_cl(ptr(dl_cl), ptr(x), c_ll(ld(x)), ptr(w), ptr(dx), c_ll(ld(dx)), c_int(1 if accumulate else 0),
                                   ptr(dw), ptr(db), c_int(n), c_ll(d * h * wd), c_int(c), c_int(k), stream_ptr()))
     return dw, db
