@@ -11,9 +11,9 @@
 #include "b3d_internal.h"
 #include <algorithm>
 
-static int gt_blocks_per_sample(long long work, int threads, int N) {
+static int gt_blocks_per_sample(long long work, int threads, int N, int per_sm = 8) {
   long long b = (work + threads - 1) / threads;
-  const long long cap = std::max(1, b3d_num_sms() * 8 / std::max(1, N));
+  const long long cap = std::max(1, b3d_num_sms() * per_sm / std::max(1, N));
   return (int)std::max<long long>(1, std::min(b, cap));
 }
 
@@ -345,6 +345,62 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; }
   float db = 0.f;
+  if (nchunks == 1) {
+    // every lane owns ONE fixed 8-channel chunk.  Its 64 constants are re-read per voxel from shared memory as 16 float4
+    // broadcasts (a chunk-major copy, instead of 64 scalar reads), two voxel groups are in flight, and the arithmetic keeps the
+    // association of the generic path (the ReLU mask must agree with the forward's)
+    __shared__ __align__(16) float cst[32 * 64];   // [chunk][kind: mg rg gg mx rx gx sh wp][8]
+    for (int i = threadIdx.x; i < F8 * 64; i += blockDim.x) {
+      const int c8 = i >> 6, kind = (i >> 3) & 7, j = i & 7, c = c8 * 8 + j;
+      cst[i] = kind == 0 ? mg[c] : kind == 1 ? rg[c] : kind == 2 ? gg[c] : kind == 3 ? mx[c] : kind == 4 ? rx[c]
+             : kind == 5 ? gx[c] : kind == 6 ? sh[c] : wp[c];
+    }
+    __syncthreads();
+    const float4* cl = reinterpret_cast<const float4*>(cst + (lc < F8 ? lc : 0) * 64);
+    constexpr int UP = 2;
+    for (long long v0 = warp_id * vpw * UP; v0 < V; v0 += nwarps * vpw * UP) {
+      uint4 ra[UP], rb[UP];
+      float prv[UP], dpv[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        const bool ok = v < V && lc < F8;
+        ra[u] = ok ? ldg16_stream(gn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        rb[u] = ok ? ldg16_stream(xn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        prv[u] = ok ? __ldg(psi_raw + (long long)n * V + v) : 0.f;
+        dpv[u] = ok ? __ldg(dpsin + (long long)n * V + v) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        if (!(v < V && lc < F8)) continue;
+        const float xh = (prv[u] - mu) * rstd;
+        const float dpr = rstd * (gp * dpv[u] - m1p - xh * m2p);
+        if (lc == 0) db += dpr;
+        float a[8], b[8], o[8];
+        unpack8(ra[u], a); unpack8(rb[u], b);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const float4 kmg = cl[0 + hf], krg = cl[2 + hf], kgg = cl[4 + hf], kmx = cl[6 + hf], krx = cl[8 + hf], kgx = cl[10 + hf],
+                       ksh = cl[12 + hf], kwp = cl[14 + hf];
+          const float vmg[4] = {kmg.x, kmg.y, kmg.z, kmg.w}, vrg[4] = {krg.x, krg.y, krg.z, krg.w}, vgg[4] = {kgg.x, kgg.y, kgg.z, kgg.w};
+          const float vmx[4] = {kmx.x, kmx.y, kmx.z, kmx.w}, vrx[4] = {krx.x, krx.y, krx.z, krx.w}, vgx[4] = {kgx.x, kgx.y, kgx.z, kgx.w};
+          const float vsh[4] = {ksh.x, ksh.y, ksh.z, ksh.w}, vwp[4] = {kwp.x, kwp.y, kwp.z, kwp.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = hf * 4 + jj;
+            const float xg = (a[j] - vmg[jj]) * vrg[jj], xx = (b[j] - vmx[jj]) * vrx[jj];
+            const float q = fmaf(xg, vgg[jj], fmaf(xx, vgx[jj], vsh[jj]));
+            const float dzv = q > 0.f ? dpr * vwp[jj] : 0.f;
+            o[j] = dzv;
+            const float qq = fmaxf(q, 0.f);
+            a0[j] += dzv; a1[j] = fmaf(dzv, xg, a1[j]); a2[j] = fmaf(dzv, xx, a2[j]); a3[j] = fmaf(dpr, qq, a3[j]);
+          }
+        }
+        stg16(dzn + v * F + lc * 8, pack8(o));
+      }
+    }
+  } else
   for (long long v0 = warp_id * vpw; v0 < V; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     if (v >= V) continue;
@@ -492,7 +548,7 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
                      void* dz, double* sums_g, double* sums_x, float* dwpsi, float* dbpsi, float* dgpsi, float* dbpsi_n,
                      int N, long long V, int F, float eps, void* stream) {
   B3D_REQUIRE(F % 8 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_bwd: F=%d unsupported", F);
-  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
+  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);   // (a single resident wave of long CTAs measured 30 % slower)
   static const cudaError_t attr = cudaFuncSetAttribute(gate_psi_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * (int)sizeof(float));   // one-time, thread-safe
   B3D_CHECK_CUDA(attr);
   gate_psi_bwd_kernel<<<grid, 256, 16 * F * sizeof(float), (cudaStream_t)stream>>>(

@@ -338,67 +338,101 @@ __global__ void __launch_bounds__(256) final_head_fwd_kernel(const bf16* __restr
 }
 
 // backward phase 1: red[0..F2) Σdz, [F2..2F2) Σdz*xhat, then dW2 [K][F2], then db2 [K]   (double atomics, caller zeroes)
+// F2/8 lanes share a voxel, each owning one 16-byte chunk of h: 52 accumulators per thread instead of 100 (the thread-per-voxel
+// version needed 160 registers -> one CTA per SM, one voxel in flight per thread: 1.3 TB/s), four voxel groups in flight.
 template <int F2>
-__global__ void __launch_bounds__(256) final_head_bwd_reduce_kernel(const float* __restrict__ dl, const bf16* __restrict__ h,
+__global__ void __launch_bounds__(256, 2) final_head_bwd_reduce_kernel(const float* __restrict__ dl, const bf16* __restrict__ h,
                                                                     long long ldh, const float* __restrict__ bn,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     const float* __restrict__ w2, double* __restrict__ red, int N,
                                                                     long long V) {
   constexpr int NR = 2 * F2 + KCLS * F2 + KCLS;
-  __shared__ float s_mean[F2], s_rstd[F2], s_g[F2], s_bt[F2], s_w[KCLS * F2];
+  constexpr int LPV = F2 / 8;          // lanes per voxel
+  constexpr int VPW = 32 / LPV;        // voxels per warp pass
+  constexpr int UF = 2;
   __shared__ double s_red[NR];   // fp64: warp arrival order cannot change the BatchNorm-backward sums
-  if (threadIdx.x < F2) {
-    s_mean[threadIdx.x] = bn[threadIdx.x]; s_rstd[threadIdx.x] = bn[F2 + threadIdx.x];
-    s_g[threadIdx.x] = gamma[threadIdx.x]; s_bt[threadIdx.x] = beta[threadIdx.x];
-  }
-  for (int i = threadIdx.x; i < KCLS * F2; i += blockDim.x) s_w[i] = w2[i];
   for (int i = threadIdx.x; i < NR; i += blockDim.x) s_red[i] = 0.0;
-  __syncthreads();
-  float a_dz[F2], a_dzx[F2], a_w[KCLS][F2], a_b[KCLS];
+  const int lane = threadIdx.x & 31;
+  const int lc = lane % LPV, lv = lane / LPV;
+  __shared__ __align__(16) float s_w[LPV * KCLS * 8];   // [chunk][class][8]: read back as float4 broadcasts
+  for (int i = threadIdx.x; i < LPV * KCLS * 8; i += blockDim.x) {
+    const int c8 = i / (KCLS * 8), k = (i / 8) % KCLS, j = i & 7;
+    s_w[i] = w2[k * F2 + c8 * 8 + j];
+  }
+  float k_mean[8], k_rstd[8], k_g[8], k_bt[8];
 #pragma unroll
-  for (int c = 0; c < F2; ++c) { a_dz[c] = 0.f; a_dzx[c] = 0.f; }
+  for (int j = 0; j < 8; ++j) {
+    const int c = lc * 8 + j;
+    k_mean[j] = bn[c]; k_rstd[j] = bn[F2 + c]; k_g[j] = gamma[c]; k_bt[j] = beta[c];
+  }
+  __syncthreads();
+  const float4* wl = reinterpret_cast<const float4*>(s_w + lc * KCLS * 8);
+  float a_dz[8], a_dzx[8], a_w[KCLS][8], a_b[KCLS];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a_dz[j] = 0.f; a_dzx[j] = 0.f; }
 #pragma unroll
   for (int k = 0; k < KCLS; ++k) {
     a_b[k] = 0.f;
 #pragma unroll
-    for (int c = 0; c < F2; ++c) a_w[k][c] = 0.f;
+    for (int j = 0; j < 8; ++j) a_w[k][j] = 0.f;
   }
   const long long total = (long long)N * V;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long n = i / V, v = i - n * V;
-    float g[KCLS];
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i0 = warp_id * VPW * UF; i0 < total; i0 += nwarps * VPW * UF) {
+    uint4 raw[UF];
+    float g[UF][KCLS];
 #pragma unroll
-    for (int k = 0; k < KCLS; ++k) { g[k] = __ldg(dl + (n * KCLS + k) * V + v); a_b[k] += g[k]; }
+    for (int u = 0; u < UF; ++u) {
+      const long long i = i0 + u * VPW + lv;
+      const bool ok = i < total;
+      const long long n = ok ? i / V : 0, v = ok ? i - n * V : 0;
+      raw[u] = ok ? ldg16_stream(h + i * ldh + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int c8 = 0; c8 < F2 / 8; ++c8) {
+      for (int k = 0; k < KCLS; ++k) g[u][k] = ok ? __ldg(dl + (n * KCLS + k) * V + v) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      const long long i = i0 + u * VPW + lv;
+      if (i >= total) continue;
       float a[8];
-      unpack8(ldg16_stream(h + i * ldh + c8 * 8), a);
+      unpack8(raw[u], a);
+      if (lc == 0) {
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k) a_b[k] += g[u][k];
+      }
+      float dr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < KCLS; ++k) {
+        const float4 w0 = wl[2 * k], w1 = wl[2 * k + 1];
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dr[j] = fmaf(g[u][k], wv[j], dr[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = c8 * 8 + j;
-        const float xh = (a[j] - s_mean[c]) * s_rstd[c];
-        const float hn = fmaf(xh, s_g[c], s_bt[c]);
+        const float xh = (a[j] - k_mean[j]) * k_rstd[j];
+        const float hn = fmaf(xh, k_g[j], k_bt[j]);
         const float r = fmaxf(hn, 0.f);
-        float dr = 0.f;
 #pragma unroll
-        for (int k = 0; k < KCLS; ++k) { dr = fmaf(g[k], s_w[k * F2 + c], dr); a_w[k][c] = fmaf(g[k], r, a_w[k][c]); }
-        const float dz = hn > 0.f ? dr : 0.f;
-        a_dz[c] += dz; a_dzx[c] += dz * xh;
+        for (int k = 0; k < KCLS; ++k) a_w[k][j] = fmaf(g[u][k], r, a_w[k][j]);
+        const float dz = hn > 0.f ? dr[j] : 0.f;
+        a_dz[j] += dz; a_dzx[j] += dz * xh;
       }
     }
   }
-  const int lane = threadIdx.x & 31;
+  // fold the lanes that own the same chunk (stride LPV), then one shared fp64 atomic per warp and value
 #pragma unroll
-  for (int c = 0; c < F2; ++c) {
-    const float s1 = warp_sum(a_dz[c]), s2 = warp_sum(a_dzx[c]);
-    if (lane == 0) { atomicAdd(&s_red[c], (double)s1); atomicAdd(&s_red[F2 + c], (double)s2); }
+  for (int j = 0; j < 8; ++j) {
+    const float s1 = warp_sum_mod(a_dz[j], LPV), s2 = warp_sum_mod(a_dzx[j], LPV);
+    if (lane < LPV) { atomicAdd(&s_red[lc * 8 + j], (double)s1); atomicAdd(&s_red[F2 + lc * 8 + j], (double)s2); }
   }
 #pragma unroll
   for (int k = 0; k < KCLS; ++k) {
 #pragma unroll
-    for (int c = 0; c < F2; ++c) {
-      const float s = warp_sum(a_w[k][c]);
-      if (lane == 0) atomicAdd(&s_red[2 * F2 + k * F2 + c], (double)s);
+    for (int j = 0; j < 8; ++j) {
+      const float sv = warp_sum_mod(a_w[k][j], LPV);
+      if (lane < LPV) atomicAdd(&s_red[2 * F2 + k * F2 + lc * 8 + j], (double)sv);
     }
     const float sb = warp_sum(a_b[k]);
     if (lane == 0) atomicAdd(&s_red[2 * F2 + KCLS * F2 + k], (double)sb);

@@ -523,7 +523,8 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
                       const float* gamma, const float* beta, int G, int relu, double* sums, int N, long long V, int C,
                       float eps, void* stream) {
   B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0, "gn_bwd_reduce: bad C=%d G=%d", C, G);
-  const int per_sample = std::max(1, std::min(ew_blocks(V * (C / 8), GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
+  // exactly one resident wave (3 CTAs per SM): 4 per SM ran 1.33 waves, the last one a third full
+  const int per_sample = std::max(1, std::min(ew_blocks(V * (C / 8), GN_THREADS * 8), b3d_num_sms() * 3 / std::max(1, N)));
   dim3 grid(per_sample, N);
   const size_t smem = 8 * (size_t)C * sizeof(float);   // 4C floats + 2C doubles
   static const cudaError_t attr = [] {   // one-time, thread-safe; up to 64 KB at C = GN_MAXC (the wide model's 2048-channel concat buffers)
@@ -567,7 +568,7 @@ int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ld
   const int C8 = C / 8;
   if (C > 512 || (GN_THREADS % C8) != 0) return 1;
   cudaStream_t st = (cudaStream_t)stream;
-  const int per_sample = std::max(1, std::min(ew_blocks(V * C8, GN_THREADS * 8), b3d_num_sms() * 4 / std::max(1, N)));
+  const int per_sample = std::max(1, std::min(ew_blocks(V * C8, GN_THREADS * 8), b3d_num_sms() * 2 / std::max(1, N)));   // one resident wave
   // OCC = resident blocks per SM the register allocation is capped for: 2 (121/126 registers, no spills; ncu: 25 % warps
   // active, 4.3-4.6 TB/s, profiles/ncu_r1_gn_bwd_dual.txt) or 3 (80 registers, ~150 bytes of spills).  Measured at
   // 2x128^3x32 (scripts/gn_dual_once.py): OCC 2 0.485 ms, OCC 3 0.635 ms — the spills cost more than the extra warps hide,
