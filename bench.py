@@ -285,7 +285,7 @@ def main():
     model = U.UNet3D(4, 4, features=feats, dropout_rate=0.2).to(dev)
     model.train()
     crit = U.DeepSupervisionLoss3D()
-    net = DataParallel(model) if world > 1 else model
+    net = DataParallel(model, bucket_mb=float(os.environ.get("B3D_BUCKET_MB", "32"))) if world > 1 else model
     use_graph = not os.environ.get("B3D_NO_GRAPH")
     opt = U.make_adamw(model, lr=1e-4, weight_decay=1e-4, capturable=use_graph)
 

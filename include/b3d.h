@@ -24,9 +24,11 @@ int b3d_version(void);
 const char* b3d_last_error_string(void);             /* thread-local */
 int b3d_check_device(void);                          /* 0 iff current device is compute capability 10.x */
 long long b3d_launch_count(void);                    /* kernels launched by this library so far (process-wide, atomic) */
-/* 1: ONE MMA-issuing warp instead of two ping-pong issuers in the z-marching 3x3x3 kernel -> fixed fp32 accumulation order ->
- * the forward pass and the input gradients are bit-reproducible run to run (default 0, or env B3D_ORDERED_ISSUE; the
- * reference's cuDNN path makes no such promise either).  Returns the previous setting.  Process-wide, atomic. */
+/* Issue schedule of the z-marching 3x3x3 kernel.  0 (default): two ping-pong MMA-issuing warps — fastest, but tcgen05.mma is only
+ * ordered within a thread, so the fp32 accumulation order jitters (~1e-7 of the bf16 outputs differ by an ulp between runs).
+ * 2: ONE issuing thread fed by a scout warp that does the barrier waits and descriptor arithmetic -> forward pass and input
+ * gradients bit-reproducible run to run, ~2 % slower per step.  1: one issuing warp without the scout (~13 % slower; kept for
+ * comparison).  Default from env B3D_ORDERED_ISSUE.  Returns the previous mode.  Process-wide, atomic. */
 int b3d_set_ordered_issue(int on);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_igemm.cu, conv_wgrad.cu) ----------------------------------- */

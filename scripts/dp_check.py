@@ -8,7 +8,7 @@ import b3d  # noqa
 import unet3d_b200 as U
 from unet3d_b200.parallel import DataParallel
 from unet3d_b200 import _lib
-_lib.set_ordered_issue(True)   # bit-reproducible forward / input gradients: what is left is the fp32-atomic jitter of the wgrad flush
+_lib.set_ordered_issue(2)   # bit-reproducible forward / input gradients: what is left is the fp32-atomic jitter of the wgrad flush
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)

@@ -15,8 +15,8 @@ for (n, s, cin, cout) in ((1, 128, 16, 32), (2, 128, 32, 32), (2, 64, 64, 64)):
     wp, kp, rows = ops.pack_weight(w, ops.PACK_FPROP)
     ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, padding=1).permute(0, 2, 3, 4, 1)
     scale = float(ref.abs().max())
-    for mode in (0, 1):
-        _lib.set_ordered_issue(bool(mode))
+    for mode in (0, 1, 2):
+        _lib.set_ordered_issue(mode)
         outs = []
         for _ in range(6):
             y, st = ops.conv_fprop(x, wp, rows, cout, 3, groups=8)
@@ -26,6 +26,13 @@ for (n, s, cin, cout) in ((1, 128, 16, 32), (2, 128, 32, 32), (2, 64, 64, 64)):
         maxd = [float((o[0].float() - outs[0][0].float()).abs().max()) for o in outs[1:]]
         err = [float((o[0].float() - ref).abs().max()) / scale for o in outs]
         sd = [float(((o[1] - outs[0][1]).abs() / (outs[0][1].abs() + 1)).max()) for o in outs[1:]]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.conv_fprop(x, wp, rows, cout, 3, groups=8)
+        e1.record(); torch.cuda.synchronize()
+        print("   %.3f ms per launch" % (e0.elapsed_time(e1) / 10))
         print("conv %dx%d^3 %d->%d ordered=%d: differing elements vs run 0: %s of %d, max |d| %s, max err vs fp32 / scale %s, "
               "stats rel diff %s" % (n, s, cin, cout, mode, ndiff, outs[0][0].numel(), ["%.2e" % v for v in maxd],
                                      ["%.2e" % v for v in err], ["%.1e" % v for v in sd]), flush=True)

@@ -69,6 +69,7 @@ def require_device(device):
 
 
 def set_ordered_issue(on):
-    """Bit-reproducible forward / input gradients (one MMA issuer in the z-marching conv kernel instead of two ping-pong
-    issuers, whose accumulation order jitters by an fp32 ulp from run to run).  Returns the previous setting."""
-    return bool(lib().b3d_set_ordered_issue(c_int(1 if on else 0)))
+    """Bit-reproducible forward / input gradients: ONE MMA-issuing thread in the z-marching conv kernel instead of two ping-pong
+    issuers, whose accumulation order jitters by an fp32 ulp from run to run.  0 / False: two issuers; 1 / True: one issuer;
+    2: one issuer fed by a scout warp that does the barrier waits and descriptor arithmetic.  Returns the previous mode."""
+    return int(lib().b3d_set_ordered_issue(c_int(int(on))))

@@ -25,6 +25,7 @@
 
 #define ZS_THREADS 352   // warp 0 TMA, warps 1 and 6 MMA issuers (ping-pong), warps 2-5 and 7-10 epilogue (even / odd planes)
 #define ZS_MAXSTAGES 8
+#define ZS_Q 8            // depth of the scout -> issuer record queue
 #define ZS_BW 10
 #define ZS_BH 18
 #define ZS_BOX 180
@@ -90,14 +91,19 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 32);
   // fp64 so that the order in which the 8 epilogue warps add their (fixed-order fp32) partial sums cannot change the result
   double* s_stats = reinterpret_cast<double*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 48);  // [2 * 64]
+  // scout -> issuer queue (P.solo == 2): ZS_Q records of 12 words + ready / free barriers
+  uint32_t* q_rec = reinterpret_cast<uint32_t*>(aux + 16 * ZS_MAXSTAGES + 16 * 32 + 48 + 128 * 8);
+  const uint32_t rdy0 = smem_u32(q_rec + ZS_Q * 12);
+  const uint32_t fre0 = rdy0 + 8 * ZS_Q;
 
   if (threadIdx.x == 0) {
     if (sW & 1023u) { if (P.err) atomicExch(P.err, 29); __trap(); }
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     for (int i = 0; i < R; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
     mbar_init(wfull, 1);
-    mbar_init(wfree, P.solo ? 1 : 2);
+    mbar_init(wfree, P.solo ? 1 : 2);   // committed by every warp that issues MMAs
     mbar_init(hs0, 1); mbar_init(hs0 + 8, 1);
+    for (int i = 0; i < ZS_Q; ++i) { mbar_init(rdy0 + 8 * i, 1); mbar_init(fre0 + 8 * i, 1); }
     mbar_fence_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 192) s_stats[threadIdx.x - 64] = 0.0;
@@ -155,6 +161,129 @@ __global__ void __launch_bounds__(ZS_THREADS, 1) zs_kernel(const __grid_constant
           if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
       }
+    }
+  } else if (P.solo == 2 && warp == 6) {
+    // ======================= scout (ordered-issue mode 2) =======================
+    // Does everything of the issue loop EXCEPT issuing: the barrier waits (stage full, accumulator slot drained + zeroed,
+    // weights resident), the ring arithmetic and the descriptor bases, and hands the single issuing thread one 12-word record
+    // per (plane, K chunk).  tcgen05.mma is only ordered within a thread, so ONE issuer makes the fp32 accumulation order — and
+    // with it the forward pass — bit-reproducible; the scout gives that thread the overlap the second issuer provided.
+    const uint32_t idesc1 = umma_idesc_bf16(128, COUT, 0, 0);
+    const uint32_t idesc2 = umma_idesc_bf16(128, 2 * COUT, 0, 0);
+    const uint32_t idesc3 = umma_idesc_bf16(128, 3 * COUT, 0, 0);
+    constexpr uint32_t RM = R - 1;
+    constexpr uint32_t LBO1 = 1u << 16;
+    uint32_t s = 0, ph = 0, g0 = 0, q = 0, qph = 0;
+    int cur_nb = -1;
+    uint32_t wloads = 0;
+    long long pos = lo;
+    ZsSeg sg;
+    auto wait_fresh = [&](uint32_t g) { mbar_wait(tempty0 + 8 * (g & RM), (((g / R) & 1u) ^ 1u), P.err, 24); };
+    auto post = [&](uint32_t a16, uint32_t w16, uint32_t w16b, uint32_t d1, uint32_t d2, uint32_t id1, uint32_t id2, uint32_t flags) {
+      mbar_wait(fre0 + 8 * q, qph ^ 1u, P.err, 27);
+      if (lane == 0) {
+        uint32_t* r = q_rec + q * 12;
+        r[0] = a16; r[1] = w16; r[2] = w16b; r[3] = d1; r[4] = d2; r[5] = id1; r[6] = id2; r[7] = flags;
+        mbar_arrive(rdy0 + 8 * q);   // release: the record (and every wait above) is visible to the issuer
+      }
+      __syncwarp();
+      if (++q == ZS_Q) { q = 0; qph ^= 1u; }
+    };
+    while (zs_next_seg(pos, hi, P.D, sg)) {
+      const int nb = sg.col / P.tiles_per_nb;
+      if (nb != cur_nb) {
+        mbar_wait(wfull, wloads & 1u, P.err, 22);
+        cur_nb = nb; ++wloads;
+      }
+      const int L = sg.zb - sg.za;
+      const int i_min = sg.za > 0 ? 0 : 1;
+      const int i_max = sg.zb < P.D ? L + 1 : L;
+      bool release_w = false;
+      if (P.n_blocks > 1) {
+        long long p2 = pos; ZsSeg nx;
+        release_w = zs_next_seg(p2, hi, P.D, nx) && nx.col / P.tiles_per_nb != nb;
+      }
+      for (int i = i_min; i <= i_max; ++i) {
+        const int o_hi = i < L - 1 ? i : L - 1;
+        const int o_lo = i - 2 > 0 ? i - 2 : 0;
+        const int cnt = o_hi - o_lo + 1;
+        const int kd0 = i - o_hi;
+        if (i == i_min) { for (int o = o_lo; o <= o_hi; ++o) wait_fresh(g0 + (uint32_t)o); }
+        else if (i <= L - 1) wait_fresh(g0 + (uint32_t)i);
+        const uint32_t m = (g0 + (uint32_t)o_hi) & RM;
+        const uint32_t p0 = RM - m;
+        const int run1 = (cnt <= (int)m + 1) ? cnt : (int)m + 1;
+        const int run2 = cnt - run1;
+        const uint32_t d1 = tmem_base + p0 * COUT;
+        const uint32_t d2 = tmem_base;
+        const uint32_t id1 = run1 == 3 ? idesc3 : (run1 == 2 ? idesc2 : idesc1);
+        const uint32_t id2 = run2 == 2 ? idesc2 : idesc1;
+        for (int kc = 0; kc < P.k_chunks; ++kc) {
+          mbar_wait(full0 + 8 * s, ph, P.err, 23);
+          const uint32_t a16 = ((sA + s * A_STAGE) >> 4) | LBO1;
+          const uint32_t w16 = (((sW + kc * W_CHUNK) >> 4) + (uint32_t)(kd0 * COUT) * rb16) | LBO1;
+          const uint32_t w16b = w16 + (uint32_t)(run1 * COUT) * rb16;
+          uint32_t flags = (run2 > 0 ? 1u : 0u) | (s << 4);
+          if (kc == P.k_chunks - 1) {
+            uint32_t nc = 0, slots = 0;
+            if (i == i_max) { for (int o = o_lo; o <= o_hi; ++o) { slots |= ((g0 + (uint32_t)o) & RM) << (5 * nc); ++nc; } }
+            else if (i >= 2) { slots = (g0 + (uint32_t)(i - 2)) & RM; nc = 1; }
+            flags |= (nc << 8) | (slots << 10);
+            if (i == i_max && release_w) flags |= 4u;
+          }
+          post(a16, w16, w16b, d1, d2, id1, id2, flags);
+          if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+        }
+      }
+      g0 += (uint32_t)L;
+    }
+    post(0u, 0u, 0u, 0u, 0u, 0u, 0u, 8u);   // END
+  } else if (P.solo == 2 && warp == 1) {
+    // ======================= the single issuer (ordered-issue mode 2) =======================
+    const uint64_t hiA = umma_desc_hi_sw((uint32_t)ZS_BW * RB, LT);
+    const uint64_t hiB = umma_desc_hi_sw(8u * RB, LT);
+    uint32_t q = 0, qph = 0;
+    for (;;) {
+      mbar_wait(rdy0 + 8 * q, qph, P.err, 28);
+      tc_fence_after();
+      const uint32_t* r = q_rec + q * 12;
+      const uint32_t a16 = r[0], w16 = r[1], w16b = r[2], d1 = r[3], d2 = r[4], id1 = r[5], id2 = r[6], flags = r[7];
+      if (flags & 8u) break;
+      if (elect_one()) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+            for (int k = 0; k < NK16; ++k) {
+              const uint32_t alo = a16 + (uint32_t)((kh * ZS_BW + kw) * rb16 + k * 2);
+              const uint32_t blo = w16 + (uint32_t)(((kh * 3 + kw) * 3 * COUT) * rb16 + k * 2);
+              umma_bf16_ss(d1, hiA | alo, hiB | blo, id1, 1u);
+            }
+          }
+        }
+        if (flags & 1u) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int k = 0; k < NK16; ++k) {
+                const uint32_t alo = a16 + (uint32_t)((kh * ZS_BW + kw) * rb16 + k * 2);
+                const uint32_t blo = w16b + (uint32_t)(((kh * 3 + kw) * 3 * COUT) * rb16 + k * 2);
+                umma_bf16_ss(d2, hiA | alo, hiB | blo, id2, 1u);
+              }
+            }
+          }
+        }
+        umma_commit(empty0 + 8 * ((flags >> 4) & 15u));
+        const uint32_t nc = (flags >> 8) & 3u;
+        for (uint32_t c = 0; c < nc; ++c) umma_commit(tfull0 + 8 * ((flags >> (10 + 5 * c)) & 31u));
+        if (flags & 4u) umma_commit(wfree);
+        mbar_arrive(fre0 + 8 * q);   // the record has been consumed
+      }
+      __syncwarp();
+      if (++q == ZS_Q) { q = 0; qph ^= 1u; }
     }
   } else if (warp == 1 || warp == 6) {
     // ======================= MMA issuers (warp-uniform control flow, one elected lane issues) =======================
@@ -421,7 +550,7 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
   const int RB = KC * 2;
   const int k_chunks = Cin / KC;
   const uint32_t a_stage = (uint32_t)(ZS_BOX * RB + 1023) / 1024 * 1024;
-  const size_t aux_bytes = 16 * ZS_MAXSTAGES + 16 * 32 + 32 + 128 * 8 + 64;
+  const size_t aux_bytes = 16 * ZS_MAXSTAGES + 16 * 32 + 32 + 128 * 8 + 64 + ZS_Q * 64;
   const size_t budget = 227 * 1024 - 1024 - aux_bytes;
   int COUT = 0, stages = 0;
   const int forced = B3D_ENV_INT("B3D_ZS_COUT");
@@ -450,7 +579,7 @@ int b3d_try_zs(const void* x, long long ldx, const void* wpack, int w_rows, cons
   P.tiles_x = (W + 7) / 8; P.tiles_y = (H + 15) / 16; P.n_blocks = CoutPad / COUT;
   P.tiles_per_nb = N * P.tiles_x * P.tiles_y;
   P.k_chunks = k_chunks; P.stages = stages;
-  P.solo = g_b3d_ordered_issue.load() ? 1 : 0;
+  P.solo = g_b3d_ordered_issue.load();   // 0: two ping-pong issuers, 1: one issuer, 2: one issuer fed by a scout warp
   P.total_steps = (long long)P.tiles_per_nb * P.n_blocks * D;
   P.out = (bf16*)y; P.ld_out = ldy; P.bias = bias;
   P.stats = stats; P.cpg = cpg > 0 ? cpg : 16; P.stats_groups = stats_groups; P.stats_batch = stats_batch; P.err = err_flag;

@@ -75,7 +75,7 @@ const char* b3d_last_error_string() { return g_err; }
 int b3d_version() { return 100; }
 long long b3d_launch_count() { return g_b3d_launches.load(); }
 // 1: bit-reproducible forward / input gradients (single MMA issuer in the z-marching conv kernel); returns the old value
-int b3d_set_ordered_issue(int on) { return g_b3d_ordered_issue.exchange(on ? 1 : 0); }
+int b3d_set_ordered_issue(int on) { return g_b3d_ordered_issue.exchange(on < 0 ? 0 : (on > 2 ? 2 : on)); }
 // 0 if the current device is sm_100 (B200); negative otherwise — callers must fail loudly, there is no fallback.
 int b3d_check_device() {
   int dev = 0, major = 0, minor = 0;

@@ -98,6 +98,7 @@ def new_act(n, d, h, w, c, device, zero=False):
 # ---------------------------------------------------------------------------------------------------------------
 _ARENA_BYTES = 1 << 18
 _arenas = {}
+_arena_lock = __import__("threading").Lock()   # the reference serves from threaded Flask workers (main.py:1059)
 
 
 def zeros_scratch(shape, dtype, device):
@@ -109,12 +110,13 @@ def zeros_scratch(shape, dtype, device):
         return torch.zeros(shape, dtype=dtype, device=device)
     # an arena filled during a graph capture belongs to that graph (and one filled eagerly is not re-zeroed by a replay)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream, torch.cuda.is_current_stream_capturing())
-    a = _arenas.get(key)
-    if a is None or a[1] + nbytes > _ARENA_BYTES:
-        a = [torch.zeros(_ARENA_BYTES, dtype=torch.uint8, device=device), 0]
-        _arenas[key] = a
-    off = a[1]
-    a[1] = off + nbytes
+    with _arena_lock:   # bump allocation must be atomic across host threads
+        a = _arenas.get(key)
+        if a is None or a[1] + nbytes > _ARENA_BYTES:
+            a = [torch.zeros(_ARENA_BYTES, dtype=torch.uint8, device=device), 0]
+            _arenas[key] = a
+        off = a[1]
+        a[1] = off + nbytes
     return a[0][off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
 
 

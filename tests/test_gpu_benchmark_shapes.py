@@ -115,7 +115,7 @@ def test_ordered_issue_mode_is_bit_reproducible_at_128():
     model.eval()
     with torch.no_grad():
         c = model(xd).clone()          # default mode (two ping-pong issuers)
-    prev = _lib.set_ordered_issue(True)
+    prev = _lib.set_ordered_issue(2)
     try:
         with torch.no_grad():
             a, b = model(xd).clone(), model(xd).clone()

@@ -322,7 +322,7 @@ def test_run_to_run_reproducibility():
     crit = U.DeepSupervisionLoss3D()
     runs = []
     from unet3d_b200 import _lib
-    prev = _lib.set_ordered_issue(True)
+    prev = _lib.set_ordered_issue(2)
     try:
         for _ in range(3):
             model.zero_grad(set_to_none=True)
