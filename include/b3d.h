@@ -104,6 +104,9 @@ int b3d_relu_adaptive_avgpool(const void* x, long long ldx, float* out, int N, i
                               int OW, int relu, void* stream);
 int b3d_pool_bwd(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
                  long long lddx, int accumulate, int N, int D, int H, int W, int C, void* stream);
+/* same, plus an optional per-(sample, channel) constant cadd fp32 [N][C] added to dx in the same pass (accumulate mode) */
+int b3d_pool_bwd_add(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
+                     long long lddx, int accumulate, const float* cadd, int N, int D, int H, int W, int C, void* stream);
 int b3d_to_ndhwc_bf16(const float* x, void* out, long long ldo, int N, int Cin, long long V, int Cpad, void* stream);
 int b3d_to_ncdhw_f32(const void* x, long long ldx, float* out, int N, int C, long long V, void* stream);
 int b3d_channel_sum(const void* x, long long ldx, double* sums, int N, long long V, int C, void* stream);

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256) relu_adaptive_avgpool_kernel(const bf16* 
 template <bool ACC>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ mask,
                                                        const bf16* __restrict__ dy, long long lddy, bf16* __restrict__ dx,
-                                                       long long lddx, int N, int D, int H, int W, int C) {
+                                                       long long lddx, const float* __restrict__ cadd, int N, int D, int H, int W,
+                                                       int C) {
   const int C8 = C >> 3;
   const int Do = D / 2, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Do * Ho * Wo * C8;
@@ -143,6 +144,11 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const bf16* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] *= mask[(long long)n * C + c0 + j];
     }
+    float ca[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ACC && cadd) {   // per-(sample, channel) constant owed to the running gradient (the gate's channel-attention branch)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ca[j] = cadd[(long long)n * C + c0 + j];
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int a = k >> 2, b = (k >> 1) & 1, c = k & 1;
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const bf16* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float val = (arg[j] == k) ? g[j] : 0.f;
-        o[j] = ACC ? o[j] + val : val;
+        o[j] = ACC ? o[j] + val + ca[j] : val;
       }
       stg16(dx + vox * lddx + c0, pack8(o));
     }
@@ -289,12 +295,23 @@ int b3d_relu_adaptive_avgpool(const void* x, long long ldx, float* out, int N, i
   return B3D_OK;
 }
 
+// cadd (optional, fp32 [N][C], accumulate mode only): a per-(sample, channel) constant added to dx in the same pass — the
+// channel-attention branch of the attention gate contributes such a constant to the skip gradient (main.py:270-276,297).
+int b3d_pool_bwd_add(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
+                     long long lddx, int accumulate, const float* cadd, int N, int D, int H, int W, int C, void* stream);
+
 int b3d_pool_bwd(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
                  long long lddx, int accumulate, int N, int D, int H, int W, int C, void* stream) {
+  return b3d_pool_bwd_add(x, ldx, mask, dy, lddy, dx, lddx, accumulate, nullptr, N, D, H, W, C, stream);
+}
+
+int b3d_pool_bwd_add(const void* x, long long ldx, const float* mask, const void* dy, long long lddy, void* dx,
+                     long long lddx, int accumulate, const float* cadd, int N, int D, int H, int W, int C, void* stream) {
   B3D_REQUIRE(C % 8 == 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "pool_bwd: need even dims and C%%8==0");
+  B3D_REQUIRE(cadd == nullptr || accumulate, "pool_bwd: the channel constant needs accumulate mode");
   const long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (C / 8);
-  if (accumulate) { pool_bwd_kernel<true><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>( (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, N, D, H, W, C); ++g_b3d_launches; }
-  else { pool_bwd_kernel<false><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>( (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, N, D, H, W, C); ++g_b3d_launches; }
+  if (accumulate) { pool_bwd_kernel<true><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>( (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, cadd, N, D, H, W, C); ++g_b3d_launches; }
+  else { pool_bwd_kernel<false><<<ew_blocks2(total, 256), 256, 0, (cudaStream_t)stream>>>( (const bf16*)x, ldx, mask, (const bf16*)dy, lddy, (bf16*)dx, lddx, nullptr, N, D, H, W, C); ++g_b3d_launches; }
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }

@@ -77,7 +77,11 @@ def _sink(name, shape):
 
 
 def bias_grad(dy):
-    """Σ over all voxels and samples -> fp32 [C]."""
+    """Σ over all voxels and samples -> fp32 [C].  The batch is folded into the voxel axis (a view), so the per-sample sums of
+    `channel_sum` need no second reduction kernel."""
+    n, d, h, w, c = dy.shape
+    if dy.stride(0) == d * dy.stride(1):
+        return ops.channel_sum(dy.as_strided((1, n * d, h, w, c), (n * dy.stride(0), dy.stride(1), dy.stride(2), dy.stride(3), 1)))[0].float()
     return ops.channel_sum(dy).sum(dim=0).float()
 
 
@@ -181,8 +185,9 @@ def gate_fwd(g, x, p, pre, out, need_bwd):
     return out, saved
 
 
-def gate_bwd(saved, dout, p, pre, dg_add=None):
-    """Returns (dg [+ dg_add], dx, grads)."""
+def gate_bwd(saved, dout, p, pre, dg_add=None, defer_const=False):
+    """Returns (dg [+ dg_add], dx, grads).  defer_const: do not add the channel-attention branch's per-(sample, channel) constant
+    to dx here — return it as a 4th value so the caller's next pass over dx (pool_bwd) adds it for free."""
     g, x, g1r, x1r, st_g, st_x, psi_raw, st_psi, ca, z, mean = saved
     n, d, h, w, c = x.shape
     f = g1r.shape[-1]
@@ -221,6 +226,8 @@ def gate_bwd(saved, dout, p, pre, dg_add=None):
     # dg is only ever added to the gradient of the up-sampled half of the concat buffer: fuse that add (dg_add)
     dg, _ = ops.conv_fprop(dg1r_full, wgd, rowsgd, c, 1, add=dg_add)
     ops.conv_fprop(dx1r_full, wxd, rowsxd, c, 1, out=dx, add=dx)                 # dx += W_x-branch gradient, fused
+    if defer_const:
+        return dg, dx, grads, xadd
     ops.add_channel_const(dx, xadd)
     return dg, dx, grads
 
@@ -244,13 +251,13 @@ def up_gate_fwd(x_low, skip, p, idx, need_bwd):
 def up_gate_bwd(saved, dcat, p, idx):
     """Returns (dx_low, dskip, grads)."""
     x_low, gsaved, cin, c = saved
-    du, dskip, grads = gate_bwd(gsaved, dcat[..., :c], p, "ups.%d." % (idx + 1), dg_add=dcat[..., c:])
+    du, dskip, grads, xadd = gate_bwd(gsaved, dcat[..., :c], p, "ups.%d." % (idx + 1), dg_add=dcat[..., c:], defer_const=True)
     wt = p["ups.%d.weight" % idx]
     grads["ups.%d.weight" % idx] = ops.convT2_wgrad(x_low, du, cin, c, dw=_sink("ups.%d.weight" % idx, wt.shape))
     grads["ups.%d.bias" % idx] = bias_grad(du)
     wtd, _, rowsd = packed(wt, ops.PACK_CONVT_DGRAD)
     dx_low = ops.convT2_dgrad(du, wtd, rowsd, cin)
-    return dx_low, dskip, grads
+    return dx_low, (dskip, xadd), grads
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -381,8 +388,8 @@ def unet_bwd(S, dmain, ddeep, p, features, on_grads=None):
     emit(g)
     for i in reversed(range(nl)):
         skip, mask = S["pool"][i]
-        dskip = dskips[i]
-        ops.pool_bwd(skip, mask, dx, dx=dskip, accumulate=True)
+        dskip, xadd = dskips[i]   # xadd: the gate's channel-attention constant still owed to dskip, added by this pass
+        ops.pool_bwd(skip, mask, dx, dx=dskip, accumulate=True, cadd=xadd)
         if i < nl - 1 and ddeep is not None and i < len(ddeep) and ddeep[i] is not None:
             emit(ds_head_bwd(skip, ddeep[i], p, i, dskip))
         dx, g = double_conv_bwd(S["enc"][i], dskip, p, "downs.%d." % i, need_dx=(i > 0))

@@ -533,13 +533,16 @@ def relu_adaptive_avgpool(x, osize, relu=True):
     return out
 
 
-def pool_bwd(x, mask, dy, dx=None, accumulate=False):
+def pool_bwd(x, mask, dy, dx=None, accumulate=False, cadd=None):
+    """`cadd`: optional fp32 [N,C] constant added to dx in the same pass (accumulate mode; see b3d_pool_bwd_add)."""
     n, d, h, w, c = x.shape
     if dx is None:
         dx = new_act(n, d, h, w, c, x.device)
         accumulate = False
-    check(_L().b3d_pool_bwd(ptr(x), c_ll(ld(x)), ptr(mask), ptr(dy), c_ll(ld(dy)), ptr(dx), c_ll(ld(dx)),
-                            c_int(1 if accumulate else 0), c_int(n), c_int(d), c_int(h), c_int(w), c_int(c), stream_ptr()))
+        assert cadd is None
+    check(_L().b3d_pool_bwd_add(ptr(x), c_ll(ld(x)), ptr(mask), ptr(dy), c_ll(ld(dy)), ptr(dx), c_ll(ld(dx)),
+                                c_int(1 if accumulate else 0), ptr(cadd), c_int(n), c_int(d), c_int(h), c_int(w), c_int(c),
+                                stream_ptr()))
     return dx
 
 
