@@ -63,6 +63,9 @@ int b3d_conv_fprop_add(const void* x, long long ldx, const void* wpack, int w_ro
  * [Cout][Cin + Cout] = [mode-1 packed W | identity]; y may alias addend. */
 int b3d_conv1_add_mma(const void* x, long long ldx, const void* addend, long long ld_add, const void* wpack_aug, int w_rows,
                       void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);
+/* tuning hooks of the implicit-GEMM tile planner (0 = planner's choice); not used by the product path */
+int b3d_set_plan_override(int td, int th, int tw, int kc, int bn);
+const char* b3d_last_plan(void);
 int b3d_convT2_fprop(const void* x, long long ldx, const void* wpack, const float* bias, void* y, long long ldy, int N,
                      int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);
 int b3d_convT2_dgrad(const void* dy, long long lddy, const void* wpack, int w_rows, void* dx, long long lddx, int N, int D,

@@ -26,6 +26,7 @@
 #include "b3d_common.cuh"
 #include "b3d_internal.h"
 #include <algorithm>
+#include <atomic>
 #include <math.h>
 #include <type_traits>
 
@@ -457,6 +458,8 @@ __global__ void igemm_finalize_kernel(const float* __restrict__ ws, int nsplit, 
 // Host side: planner + launcher
 // ---------------------------------------------------------------------------------------------
 static const int kSmemBudget = 227 * 1024 - 2048;
+static std::atomic<int> g_plan_override[6];   // TD, TH, TW, KC, BN, verbose  (0 = planner's choice)
+static thread_local char g_last_plan[256] = "";
 
 struct IgemmPlan {
   int TD, TH, TW, KC, BN, MB, GS, stages, acc_bufs, ksplit, patch;
@@ -473,11 +476,12 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
   const int halo = ks / 2, KD = ks, KHW = ks * ks;
   const int Ktotal = chan_per_map * nmaps;
   IgemmPlan best; best.ok = false; best.cost = 1e30;
-  const int env_td = B3D_ENV_INT("B3D_TD");
-  const int env_th = B3D_ENV_INT("B3D_TH");
-  const int env_tw = B3D_ENV_INT("B3D_TW");
-  const int env_kc = B3D_ENV_INT("B3D_KC");
-  const int env_bn = B3D_ENV_INT("B3D_BN");
+  // tuning overrides: environment (read once) or b3d_set_plan_override (runtime, for in-process sweeps: scripts/plan_sweep.py)
+  const int env_td = g_plan_override[0].load() ? g_plan_override[0].load() : B3D_ENV_INT("B3D_TD");
+  const int env_th = g_plan_override[1].load() ? g_plan_override[1].load() : B3D_ENV_INT("B3D_TH");
+  const int env_tw = g_plan_override[2].load() ? g_plan_override[2].load() : B3D_ENV_INT("B3D_TW");
+  const int env_kc = g_plan_override[3].load() ? g_plan_override[3].load() : B3D_ENV_INT("B3D_KC");
+  const int env_bn = g_plan_override[4].load() ? g_plan_override[4].load() : B3D_ENV_INT("B3D_BN");
   const int bn_cands[5] = {256, 128, 64, 32, 16};
   for (int patch = B3D_ENV_FLAG("B3D_NOPATCH") ? 0 : 1; patch >= 0; --patch) {
     // patch mode: tile = TD x (16 a) x (8 b), M-block = 16 rows x 8 columns (no wasted M rows)
@@ -544,13 +548,15 @@ static IgemmPlan plan_igemm(int N, int D, int H, int W, int chan_per_map, int nm
               const double mclk = (double)MB * KHW * (KC / 16) * sps * mma_clk(BN);
               const double load_clk = (double)(a + b) * sps / 28.0;  // ~28 B/clk/SM of L2->SMEM when every SM streams
               const double epi_clk = (double)MB * (BN / 16) * (ksplit > 1 ? 100.0 : 70.0) + 300.0;
-              double item_clk = std::max(mclk, load_clk);
+              // every pipeline step is a barrier round trip of the issuing thread (~350 clk measured as the gap between KC = 16 / 4
+              // stages and KC = 32 / 2 stages plans of equal MMA and load volume: scripts/plan_sweep.py, round 2)
+              double item_clk = std::max(mclk, load_clk) + 350.0 * sps;
               item_clk = (acc_bufs == 2) ? std::max(item_clk, epi_clk) : item_clk + epi_clk;
               const long long its = items * ksplit;
               const long long waves = (its + num_sms - 1) / num_sms;
               double cost = (double)waves * item_clk + 3000.0;
               if (ksplit > 1) cost += 6000.0 + (double)N * D * H * W * CoutPad * 4.0 * (ksplit + 1) / (num_sms * 20.0);  // finalize pass
-              if (stages < 3) cost *= 1.15;
+              if (stages < 3 && KC < 32) cost *= 1.15;   // two stages are enough when one stage carries >= 2 K16 steps per tap
               if (cost < best.cost) {
                 best.ok = true; best.cost = cost; best.TD = TD; best.TH = TH; best.TW = TW; best.KC = KC; best.BN = BN;
                 best.MB = MB; best.GS = patch ? BW : 8; best.stages = stages; best.acc_bufs = acc_bufs; best.ksplit = ksplit;
@@ -666,6 +672,8 @@ static int run_igemm(const ActView* views, int nmaps, int chan_per_map, const bf
   const size_t smem = (size_t)P.stages * P.stage_bytes + std::max<size_t>((size_t)pl.over, 16 * IG_MAXSTAGES + 48 + 64 * 8 + 128) + 1024;
   B3D_REQUIRE(smem <= 227 * 1024, "igemm: smem %zu too large", smem);
   const int grid = std::min(P.num_items, num_sms);
+  snprintf(g_last_plan, sizeof(g_last_plan), "tile %dx%dx%d %s KC%d BN%d MB%d stages%d acc%d split%d items%d", P.TD, P.TH, P.TW,
+           pl.patch ? "patch" : "linear", KC, BN, P.MB, P.stages, P.acc_bufs, P.ksplit, P.num_items);
   if (B3D_ENV_FLAG("B3D_VERBOSE"))
     fprintf(stderr,
             "[b3d] igemm N%d D%d H%d W%d K=%dx%d Cout=%d(ks%d mode%d) tile %dx%dx%d %s KC%d BN%d MB%d stages%d acc%d "
@@ -775,6 +783,14 @@ int b3d_conv1_add_mma(const void* x, long long ldx, const void* addend, long lon
   return run_igemm(v, nx + na, cpm, (const bf16*)wpack_aug, w_rows, 1, 1, dd, (int)hh, ww, Cout, 0, (bf16*)y, ldy, 0, nullptr,
                    nullptr, 0, 0, 0, nullptr, 0, err_flag, (cudaStream_t)stream);
 }
+
+// Tuning hooks (not used by the product path): force tile-plan parameters of the implicit-GEMM planner (0 = planner's choice)
+// and read back the plan of this thread's last launch — scripts/plan_sweep.py sweeps plans in one process with them.
+int b3d_set_plan_override(int td, int th, int tw, int kc, int bn) {
+  g_plan_override[0] = td; g_plan_override[1] = th; g_plan_override[2] = tw; g_plan_override[3] = kc; g_plan_override[4] = bn;
+  return B3D_OK;
+}
+const char* b3d_last_plan() { return g_last_plan; }
 
 int b3d_conv_fprop(const void* x, long long ldx, const void* wpack, int w_rows, const float* bias, void* y, long long ldy,
                    int N, int D, int H, int W, int Cin, int Cout, int ks, double* stats, int groups, int stats_batch,
