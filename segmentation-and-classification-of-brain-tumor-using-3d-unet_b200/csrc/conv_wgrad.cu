@@ -329,27 +329,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 
 // dwacc fp32 [taps][Cin_pad][Cout_pad] -> reference layouts (fp32), optionally accumulating into an existing gradient
 //   mode 0: conv   dW[co][ci][tap]           mode 1: convT  dWt[ci][co][t8]
-// One block per (ci, 32 output channels): coalesced 128-byte reads of dwacc rows, smem transpose, runs of `ntaps`
-// consecutive floats on the write side.
+// One block per (FIN_CIB input channels, 32 output channels): coalesced 128-byte reads of dwacc rows, smem transpose, and on
+// the write side runs of FIN_CIB * ntaps consecutive floats per output channel (mode 0: 864 B, sector aligned when
+// Cin % 8 == 0) or 32 * ntaps per input channel (mode 1).  One input channel per block left 108-byte runs and ran the
+// 1024 x 1024 x 27 gradient at 2.3 TB/s.
+#define FIN_CIB 8
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ acc, float* __restrict__ dw, int mode,
                                                              int ntaps, int Cin, int Cout, int Cin_pad, int Cout_pad,
                                                              int accumulate) {
-  __shared__ float tile[27][33];
-  const int cob = blockIdx.x, ci = blockIdx.y;
-  const int co0 = cob * 32;
+  __shared__ float tile[FIN_CIB][27][33];
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * FIN_CIB;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int tap = w; tap < ntaps; tap += 8) {
-    const int co = co0 + lane;
-    tile[tap][lane] = (co < Cout) ? acc[((long long)tap * Cin_pad + ci) * Cout_pad + co] : 0.f;
+  const int nci = min(FIN_CIB, Cin - ci0), nco = min(32, Cout - co0);
+  for (int r = w; r < nci * ntaps; r += 8) {
+    const int tap = r / nci, cil = r - tap * nci;   // consecutive rows of one tap are adjacent in dwacc
+    tile[cil][tap][lane] = (lane < nco) ? __ldcs(acc + ((long long)tap * Cin_pad + ci0 + cil) * Cout_pad + co0 + lane) : 0.f;
   }
   __syncthreads();
-  const int nco = min(32, Cout - co0);
-  for (int idx = threadIdx.x; idx < nco * ntaps; idx += 256) {
-    const int col = idx / ntaps, tap = idx - col * ntaps;
-    const int co = co0 + col;
-    const long long o = (mode == 0) ? ((long long)co * Cin + ci) * ntaps + tap : ((long long)ci * Cout + co) * ntaps + tap;
-    const float v = tile[tap][col];
-    dw[o] = accumulate ? dw[o] + v : v;
+  if (mode == 0) {
+    const int run = nci * ntaps;
+    for (int idx = threadIdx.x; idx < nco * run; idx += 256) {
+      const int col = idx / run, j = idx - col * run;
+      const int cil = j / ntaps, tap = j - cil * ntaps;
+      const long long o = ((long long)(co0 + col) * Cin + ci0) * ntaps + j;
+      const float v = tile[cil][tap][col];
+      dw[o] = accumulate ? dw[o] + v : v;
+    }
+  } else {
+    const int run = nco * ntaps;
+    for (int idx = threadIdx.x; idx < nci * run; idx += 256) {
+      const int cil = idx / run, j = idx - cil * run;
+      const int col = j / ntaps, tap = j - col * ntaps;
+      const long long o = ((long long)(ci0 + cil) * Cout + co0) * ntaps + j;
+      const float v = tile[cil][tap][col];
+      dw[o] = accumulate ? dw[o] + v : v;
+    }
   }
 }
 
@@ -553,7 +567,7 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   if (rc < 0) return rc;
   if (rc > 0) rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
-  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, Cin_real), 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
+  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, (Cin_real + FIN_CIB - 1) / FIN_CIB), 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -578,7 +592,7 @@ int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long ldd
   if (rc < 0) return rc;
   if (rc > 0) rc = run_wgrad(x, ldx, Cin, yv, 8, N, D, H, W, Cout, 1, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
-  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, Cin), 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
+  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, (Cin + FIN_CIB - 1) / FIN_CIB), 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
