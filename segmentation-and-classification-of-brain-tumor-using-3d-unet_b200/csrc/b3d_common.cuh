@@ -99,6 +99,18 @@ __device__ __forceinline__ uint4 ldg16_stream(const void* p) {
   return r;
 }
 __device__ __forceinline__ void stg16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+// "register-lean" streaming kernels keep their per-channel coefficients in shared memory and re-read them inside the loop:
+// the volatile asm stops the compiler from hoisting the loads back into (dozens of) registers.
+__device__ __forceinline__ float2 lds2v(const float* p) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ float2 bfw(unsigned w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
+__device__ __forceinline__ unsigned wbf(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<unsigned*>(&t);
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX: shared-address conversion, mbarrier, TMA, tcgen05

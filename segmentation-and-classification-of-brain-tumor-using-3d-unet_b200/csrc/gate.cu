@@ -196,6 +196,50 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc_ca[j] = 0.f;
   float r1 = 0.f, r2 = 0.f;
+  if (nchunks == 1) {
+    // every lane owns one 16-byte chunk per voxel: UB voxel groups per iteration with all their loads issued first (one
+    // group at a time left 32 KB in flight per SM and ran at 48 % of the copy bandwidth, scripts/ew_bench.py round 2)
+    constexpr int UB = 4;
+    float cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cc[j] = sca[lc * 8 + j];
+    const float* prn = psi_raw + (long long)n * V;
+    for (long long v0 = warp_id * vpw * UB; v0 < V; v0 += nwarps * vpw * UB) {
+      uint4 ud[UB], ux[UB];
+      float pr[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        const bool ok = v < V;
+        pr[u] = ok ? __ldg(prn + v) : 0.f;
+        ud[u] = ok ? ldg16_stream(don + v * lddo + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        ux[u] = ok ? ldg16_stream(xn + v * ldx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        const float s = 1.f / (1.f + __expf(-fmaf(pr[u], a, b)));
+        const float xh = (pr[u] - mu) * rstd;
+        float d[8], xv[8], o[8];
+        unpack8(ud[u], d); unpack8(ux[u], xv);
+        float ds = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dxv = d[j] * xv[j];
+          ds = fmaf(dxv, cc[j], ds);
+          o[j] = d[j] * s * cc[j];
+          acc_ca[j] = fmaf(dxv, s, acc_ca[j]);
+        }
+        if (v < V) stg16(dxn + v * lddx + lc * 8, pack8(o));
+        for (int o2 = lanes_c >> 1; o2 > 0; o2 >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o2);
+        if (lc == 0 && v < V) {
+          const float dpn = ds * s * (1.f - s);
+          dpsin[(long long)n * V + v] = dpn;
+          r1 += dpn; r2 += dpn * xh;
+        }
+      }
+    }
+  } else
   for (long long v0 = warp_id * vpw; v0 < V; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     float ds = 0.f, s = 0.f, xh = 0.f;

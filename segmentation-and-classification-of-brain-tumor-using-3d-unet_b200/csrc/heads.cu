@@ -117,49 +117,50 @@ __global__ void __launch_bounds__(256, 2) ds_head_bwd_kernel(const float* __rest
     for (int j = 0; j < 8; ++j) gw[k][j] = 0.f;
   float gb[KCLS] = {0.f, 0.f, 0.f, 0.f};
   if (nchunks == 1 && CL) {
-    // every lane owns one 16-byte chunk per voxel: two voxel groups per iteration, all their loads (logit gradient, skip,
-    // running dskip) issued before the first FMA
-    constexpr int UB = 2;
-    float wk[KCLS][8];
-#pragma unroll
-    for (int k = 0; k < KCLS; ++k)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wk[k][j] = (lc < C8) ? sw[k * C + lc * 8 + j] : 0.f;
+    // every lane owns one 16-byte chunk per voxel: UB voxel groups per iteration, all their loads (logit gradient, skip,
+    // running dskip) issued before the first FMA; the 4 x 8 weights are re-read from shared memory two channels at a time
+    // (register-lean, see b3d_common.cuh) so that four groups fit in the register file
+    constexpr int UB = 4;
+    const float* wq = sw + lc * 8;
     for (long long v0 = warp_id * vpw * UB; v0 < NV; v0 += nwarps * vpw * UB) {
-      uint4 xa[UB], xo[UB];
+      unsigned xa[UB][4], xo[UB][4];
       float4 g4[UB];
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const long long v = v0 + u * vpw + lv;
         const bool ok = v < NV && lc < C8;
         g4[u] = ok ? __ldg(reinterpret_cast<const float4*>(dl) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xa[u] = ok ? ldg16_stream(x + v * ldx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
-        if (ACC) xo[u] = ok ? ldg16(dx + v * lddx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 t = ok ? ldg16_stream(x + v * ldx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        xa[u][0] = t.x; xa[u][1] = t.y; xa[u][2] = t.z; xa[u][3] = t.w;
+        if (ACC) {
+          const uint4 t2 = ok ? ldg16(dx + v * lddx + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+          xo[u][0] = t2.x; xo[u][1] = t2.y; xo[u][2] = t2.z; xo[u][3] = t2.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 wv[KCLS];
+#pragma unroll
+        for (int k = 0; k < KCLS; ++k) wv[k] = (lc < C8) ? lds2v(wq + k * C + 2 * q) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const float g[KCLS] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+          const float2 a = bfw(xa[u][q]);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < KCLS; ++k) { s0 = fmaf(g[k], wv[k].x, s0); s1 = fmaf(g[k], wv[k].y, s1); }
+          if (ACC) { const float2 o = bfw(xo[u][q]); s0 += o.x; s1 += o.y; }
+          xo[u][q] = wbf(s0, s1);
+#pragma unroll
+          for (int k = 0; k < KCLS; ++k) { gw[k][2 * q] = fmaf(g[k], a.x, gw[k][2 * q]); gw[k][2 * q + 1] = fmaf(g[k], a.y, gw[k][2 * q + 1]); }
+        }
       }
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const long long v = v0 + u * vpw + lv;
         if (!(v < NV && lc < C8)) continue;
-        const float g[KCLS] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
-        if (lc == 0) {
-#pragma unroll
-          for (int k = 0; k < KCLS; ++k) gb[k] += g[k];
-        }
-        float a[8], o[8];
-        unpack8(xa[u], a);
-        if (ACC) unpack8(xo[u], o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float sacc = 0.f;
-#pragma unroll
-          for (int k = 0; k < KCLS; ++k) sacc = fmaf(g[k], wk[k][j], sacc);
-          o[j] = ACC ? o[j] + sacc : sacc;
-        }
-        stg16(dx + v * lddx + lc * 8, pack8(o));
-#pragma unroll
-        for (int k = 0; k < KCLS; ++k)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gw[k][j] = fmaf(g[k], a[j], gw[k][j]);
+        stg16(dx + v * lddx + lc * 8, make_uint4(xo[u][0], xo[u][1], xo[u][2], xo[u][3]));
+        if (lc == 0) { gb[0] += g4[u].x; gb[1] += g4[u].y; gb[2] += g4[u].z; gb[3] += g4[u].w; }
       }
     }
   } else

@@ -460,6 +460,314 @@ __global__ void __launch_bounds__(GN_THREADS, OCC) gn_bwd_dual_apply_kernel(
   }
 }
 
+// ---- register-lean variants of the two dual kernels --------------------------------------------------------------------
+// The per-channel coefficients stay in shared memory and are re-read (volatile 8-byte loads, two channels at a time) inside
+// the loop instead of living in 48-64 registers per thread: ~60 registers -> four resident blocks per SM instead of two,
+// i.e. twice the loads in flight for a kernel that is purely latency x bandwidth bound (ncu round 2: 126 registers, 25 % warps
+// active, 4.6 TB/s).  Arithmetic expressions are the same as in the kernels above (bit-identical results).
+
+template <int UB>
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_dual_apply_lean_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ ya, long long ldya, const double* __restrict__ stats_a,
+    const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const double* __restrict__ sums_a,
+    const bf16* __restrict__ yb, long long ldyb, const double* __restrict__ stats_b, const float* __restrict__ gamma_b,
+    const double* __restrict__ sums_b, int G, bf16* __restrict__ dxa, long long lddxa, bf16* __restrict__ dxb, long long lddxb,
+    long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* c_S = sm; float* c_T = sm + C; float* c_Pa = sm + 2 * C; float* c_Qa = sm + 3 * C; float* c_Ra = sm + 4 * C;
+  float* c_Pb = sm + 5 * C; float* c_Qb = sm + 6 * C; float* c_Rb = sm + 7 * C;
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const double m = (double)cpg * (double)V;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float mean, rstd;
+    gn_mean_rstd(stats_a, n, G, g, m, eps, mean, rstd);
+    double sb = 0, sc2 = 0;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+      sb += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2];
+      sc2 += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2 + 1];
+    }
+    float Bg = (float)(sb / m) * rstd, Cg = (float)(sc2 / m) * rstd, kb = -mean * rstd;
+    { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }
+    c_Pa[c] = gamma_a[c] * rstd; c_Qa[c] = fmaf(kb, Cg, Bg); c_Ra[c] = rstd * Cg;
+    gn_mean_rstd(stats_b, n, G, g, m, eps, mean, rstd);
+    sb = 0; sc2 = 0;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+      sb += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2];
+      sc2 += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2 + 1];
+    }
+    Bg = (float)(sb / m) * rstd; Cg = (float)(sc2 / m) * rstd; kb = -mean * rstd;
+    c_Pb[c] = gamma_b[c] * rstd; c_Qb[c] = fmaf(kb, Cg, Bg); c_Rb[c] = rstd * Cg;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int c0 = (int)(threadIdx.x % C8) * 8;
+  const bf16* dyn = dy + (long long)n * V * lddy + c0;
+  const bf16* yan = ya + (long long)n * V * ldya + c0;
+  const bf16* ybn = yb + (long long)n * V * ldyb + c0;
+  bf16* dxan = dxa + (long long)n * V * lddxa + c0;
+  bf16* dxbn = dxb + (long long)n * V * lddxb + c0;
+  const float* kc = sm + c0;
+  const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+  long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+  for (; vox < V; vox += UB * vstep) {
+    unsigned d[UB][4], x[UB][4], z[UB][4];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long vu = (vox + u * vstep < V) ? vox + u * vstep : vox;
+      const uint4 t0 = ldg16_stream(dyn + vu * lddy), t1 = ldg16_stream(yan + vu * ldya), t2 = ldg16_stream(ybn + vu * ldyb);
+      d[u][0] = t0.x; d[u][1] = t0.y; d[u][2] = t0.z; d[u][3] = t0.w;
+      x[u][0] = t1.x; x[u][1] = t1.y; x[u][2] = t1.z; x[u][3] = t1.w;
+      z[u][0] = t2.x; z[u][1] = t2.y; z[u][2] = t2.z; z[u][3] = t2.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 S = lds2v(kc + 2 * q), T = lds2v(kc + C + 2 * q), Pa = lds2v(kc + 2 * C + 2 * q),
+                   Qa = lds2v(kc + 3 * C + 2 * q), Ra = lds2v(kc + 4 * C + 2 * q), Pb = lds2v(kc + 5 * C + 2 * q),
+                   Qb = lds2v(kc + 6 * C + 2 * q), Rb = lds2v(kc + 7 * C + 2 * q);
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]), zz = bfw(z[u][q]);
+        const float dz0 = (fmaf(xx.x, S.x, T.x) <= 0.f) ? 0.f : dd.x;
+        const float dz1 = (fmaf(xx.y, S.y, T.y) <= 0.f) ? 0.f : dd.y;
+        // d[] / x[] words are dead from here on: reuse them for the packed results
+        d[u][q] = wbf(fmaf(dz0, Pa.x, -fmaf(xx.x, Ra.x, Qa.x)), fmaf(dz1, Pa.y, -fmaf(xx.y, Ra.y, Qa.y)));
+        x[u][q] = wbf(fmaf(dd.x, Pb.x, -fmaf(zz.x, Rb.x, Qb.x)), fmaf(dd.y, Pb.y, -fmaf(zz.y, Rb.y, Qb.y)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long vu = vox + u * vstep;
+      if (vu < V) {
+        stg16(dxan + vu * lddxa, make_uint4(d[u][0], d[u][1], d[u][2], d[u][3]));
+        stg16(dxbn + vu * lddxb, make_uint4(x[u][0], x[u][1], x[u][2], x[u][3]));
+      }
+    }
+  }
+}
+
+template <int UB>
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_dual_reduce_lean_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ ya, long long ldya, const double* __restrict__ stats_a,
+    const float* __restrict__ gamma_a, const float* __restrict__ beta_a, const bf16* __restrict__ yb, long long ldyb,
+    const double* __restrict__ stats_b, int G, double* __restrict__ sums_a, double* __restrict__ sums_b, long long V, int C,
+    float eps) {
+  extern __shared__ float sm[];
+  float* c_ka = sm; float* c_kb = sm + C; float* c_S = sm + 2 * C; float* c_T = sm + 3 * C;
+  float* c_kab = sm + 4 * C; float* c_kbb = sm + 5 * C;
+  double* red = reinterpret_cast<double*>(sm + 6 * C);   // [4][C]: Σdz_a, Σdz_a·x̂a, Σdy, Σdy·x̂b
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd(stats_a, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    c_ka[c] = rstd; c_kb[c] = -mean * rstd;
+    { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }
+    gn_mean_rstd(stats_b, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    c_kab[c] = rstd; c_kbb[c] = -mean * rstd;
+    red[c] = 0.0; red[C + c] = 0.0; red[2 * C + c] = 0.0; red[3 * C + c] = 0.0;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int c0 = (int)(threadIdx.x % C8) * 8;
+  const bf16* dyn = dy + (long long)n * V * lddy + c0;
+  const bf16* yan = ya + (long long)n * V * ldya + c0;
+  const bf16* ybn = yb + (long long)n * V * ldyb + c0;
+  const float* kc = sm + c0;
+  float a1[8], a2[8], a3[8], a4[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; a4[j] = 0.f; }
+  const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+  long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+  for (; vox < V; vox += UB * vstep) {
+    unsigned d[UB][4], x[UB][4], z[UB][4];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const bool ok = vox + u * vstep < V;
+      const long long vu = ok ? vox + u * vstep : vox;
+      uint4 t0 = ldg16_stream(dyn + vu * lddy);
+      const uint4 t1 = ldg16_stream(yan + vu * ldya), t2 = ldg16_stream(ybn + vu * ldyb);
+      if (!ok) t0 = make_uint4(0u, 0u, 0u, 0u);   // a zero gradient contributes nothing to any of the four sums
+      d[u][0] = t0.x; d[u][1] = t0.y; d[u][2] = t0.z; d[u][3] = t0.w;
+      x[u][0] = t1.x; x[u][1] = t1.y; x[u][2] = t1.z; x[u][3] = t1.w;
+      z[u][0] = t2.x; z[u][1] = t2.y; z[u][2] = t2.z; z[u][3] = t2.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 ka = lds2v(kc + 2 * q), kb = lds2v(kc + C + 2 * q), S = lds2v(kc + 2 * C + 2 * q),
+                   T = lds2v(kc + 3 * C + 2 * q), kab = lds2v(kc + 4 * C + 2 * q), kbb = lds2v(kc + 5 * C + 2 * q);
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]), zz = bfw(z[u][q]);
+        const float dz0 = (fmaf(xx.x, S.x, T.x) <= 0.f) ? 0.f : dd.x;
+        const float dz1 = (fmaf(xx.y, S.y, T.y) <= 0.f) ? 0.f : dd.y;
+        a1[2 * q] += dz0; a2[2 * q] = fmaf(dz0, fmaf(xx.x, ka.x, kb.x), a2[2 * q]);
+        a3[2 * q] += dd.x; a4[2 * q] = fmaf(dd.x, fmaf(zz.x, kab.x, kbb.x), a4[2 * q]);
+        a1[2 * q + 1] += dz1; a2[2 * q + 1] = fmaf(dz1, fmaf(xx.y, ka.y, kb.y), a2[2 * q + 1]);
+        a3[2 * q + 1] += dd.y; a4[2 * q + 1] = fmaf(dd.y, fmaf(zz.y, kab.y, kbb.y), a4[2 * q + 1]);
+      }
+    }
+  }
+  const int grp = C8 < 32 ? C8 : 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a1[j] = warp_sum_mod(a1[j], grp); a2[j] = warp_sum_mod(a2[j], grp);
+    a3[j] = warp_sum_mod(a3[j], grp); a4[j] = warp_sum_mod(a4[j], grp);
+  }
+  if ((int)(threadIdx.x & 31) < grp) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[c0 + j], (double)a1[j]); atomicAdd(&red[C + c0 + j], (double)a2[j]);
+      atomicAdd(&red[2 * C + c0 + j], (double)a3[j]); atomicAdd(&red[3 * C + c0 + j], (double)a4[j]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&sums_a[((long long)n * C + c) * 2], red[c]);
+    atomicAdd(&sums_a[((long long)n * C + c) * 2 + 1], red[C + c]);
+    atomicAdd(&sums_b[((long long)n * C + c) * 2], red[2 * C + c]);
+    atomicAdd(&sums_b[((long long)n * C + c) * 2 + 1], red[3 * C + c]);
+  }
+}
+
+// register-lean single-branch kernels (fixed 8-channel chunk per thread, i.e. blockDim % (C/8) == 0): same scheme as the dual
+// ones above.  UB voxels in flight per thread; launch bounds follow the register budget of UB.
+template <bool RELU, int UB>
+__global__ void __launch_bounds__(GN_THREADS, UB >= 4 ? 3 : 4) gn_bwd_reduce_lean_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y, long long ldy,
+    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
+    double* __restrict__ sums, long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* c_ka = sm; float* c_kb = sm + C; float* c_kg = sm + 2 * C; float* c_kbe = sm + 3 * C;
+  double* red = reinterpret_cast<double*>(sm + 4 * C);
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    gn_mean_rstd(stats, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
+    c_ka[c] = rstd; c_kb[c] = -mean * rstd; c_kg[c] = gamma[c]; c_kbe[c] = beta[c];
+    red[c] = 0.0; red[C + c] = 0.0;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int c0 = (int)(threadIdx.x % C8) * 8;
+  const bf16* dyn = dy + (long long)n * V * lddy + c0;
+  const bf16* yn = y + (long long)n * V * ldy + c0;
+  const float* kc = sm + c0;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+  const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+  long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+  for (; vox < V; vox += UB * vstep) {
+    unsigned d[UB][4], x[UB][4];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const bool ok = vox + u * vstep < V;
+      const long long vu = ok ? vox + u * vstep : vox;
+      uint4 t0 = ldg16_stream(dyn + vu * lddy);
+      const uint4 t1 = ldg16_stream(yn + vu * ldy);
+      if (!ok) t0 = make_uint4(0u, 0u, 0u, 0u);
+      d[u][0] = t0.x; d[u][1] = t0.y; d[u][2] = t0.z; d[u][3] = t0.w;
+      x[u][0] = t1.x; x[u][1] = t1.y; x[u][2] = t1.z; x[u][3] = t1.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 ka = lds2v(kc + 2 * q), kb = lds2v(kc + C + 2 * q);
+      float2 kg = make_float2(0.f, 0.f), kbe = kg;
+      if (RELU) { kg = lds2v(kc + 2 * C + 2 * q); kbe = lds2v(kc + 3 * C + 2 * q); }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]);
+        const float xh0 = fmaf(xx.x, ka.x, kb.x), xh1 = fmaf(xx.y, ka.y, kb.y);
+        float dz0 = dd.x, dz1 = dd.y;
+        if (RELU && fmaf(xh0, kg.x, kbe.x) <= 0.f) dz0 = 0.f;
+        if (RELU && fmaf(xh1, kg.y, kbe.y) <= 0.f) dz1 = 0.f;
+        a1[2 * q] += dz0; a2[2 * q] = fmaf(dz0, xh0, a2[2 * q]);
+        a1[2 * q + 1] += dz1; a2[2 * q + 1] = fmaf(dz1, xh1, a2[2 * q + 1]);
+      }
+    }
+  }
+  const int grp = C8 < 32 ? C8 : 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = warp_sum_mod(a1[j], grp); a2[j] = warp_sum_mod(a2[j], grp); }
+  if ((int)(threadIdx.x & 31) < grp) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&red[c0 + j], (double)a1[j]); atomicAdd(&red[C + c0 + j], (double)a2[j]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&sums[((long long)n * C + c) * 2], red[c]);
+    atomicAdd(&sums[((long long)n * C + c) * 2 + 1], red[C + c]);
+  }
+}
+
+template <bool RELU, bool ACC, int UB>
+__global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_apply_lean_kernel(
+    const bf16* __restrict__ dy, long long lddy, const bf16* __restrict__ y, long long ldy,
+    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
+    const double* __restrict__ sums, bf16* __restrict__ dx, long long lddx, long long V, int C, float eps) {
+  extern __shared__ float sm[];
+  float* c_ka = sm; float* c_kb = sm + C; float* c_kg = sm + 2 * C; float* c_kbe = sm + 3 * C;
+  float* c_B = sm + 4 * C; float* c_C = sm + 5 * C;
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const double m = (double)cpg * (double)V;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd;
+    const int g = c / cpg;
+    gn_mean_rstd(stats, n, G, g, m, eps, mean, rstd);
+    double sb = 0, sc2 = 0;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
+      sb += (double)gamma[k] * sums[((long long)n * C + k) * 2];
+      sc2 += (double)gamma[k] * sums[((long long)n * C + k) * 2 + 1];
+    }
+    c_ka[c] = rstd; c_kb[c] = -mean * rstd; c_kg[c] = gamma[c]; c_kbe[c] = beta[c];
+    c_B[c] = (float)(sb / m) * rstd; c_C[c] = (float)(sc2 / m) * rstd;
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const int c0 = (int)(threadIdx.x % C8) * 8;
+  const bf16* dyn = dy + (long long)n * V * lddy + c0;
+  const bf16* yn = y + (long long)n * V * ldy + c0;
+  bf16* dxn = dx + (long long)n * V * lddx + c0;
+  const float* kc = sm + c0;
+  const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
+  long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
+  for (; vox < V; vox += UB * vstep) {
+    unsigned d[UB][4], x[UB][4], o[UB][4];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long vu = (vox + u * vstep < V) ? vox + u * vstep : vox;
+      const uint4 t0 = ldg16_stream(dyn + vu * lddy), t1 = ldg16_stream(yn + vu * ldy);
+      d[u][0] = t0.x; d[u][1] = t0.y; d[u][2] = t0.z; d[u][3] = t0.w;
+      x[u][0] = t1.x; x[u][1] = t1.y; x[u][2] = t1.z; x[u][3] = t1.w;
+      if (ACC) { const uint4 t2 = ldg16(dxn + vu * lddx); o[u][0] = t2.x; o[u][1] = t2.y; o[u][2] = t2.z; o[u][3] = t2.w; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 ka = lds2v(kc + 2 * q), kb = lds2v(kc + C + 2 * q), kg = lds2v(kc + 2 * C + 2 * q),
+                   kbe = lds2v(kc + 3 * C + 2 * q), kB = lds2v(kc + 4 * C + 2 * q), kC = lds2v(kc + 5 * C + 2 * q);
+      const float kA0 = kg.x * ka.x, kA1 = kg.y * ka.y;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]);
+        const float xh0 = fmaf(xx.x, ka.x, kb.x), xh1 = fmaf(xx.y, ka.y, kb.y);
+        float dz0 = dd.x, dz1 = dd.y;
+        if (RELU && fmaf(xh0, kg.x, kbe.x) <= 0.f) dz0 = 0.f;
+        if (RELU && fmaf(xh1, kg.y, kbe.y) <= 0.f) dz1 = 0.f;
+        float v0 = dz0 * kA0 - kB.x - xh0 * kC.x, v1 = dz1 * kA1 - kB.y - xh1 * kC.y;
+        if (ACC) { const float2 oo = bfw(o[u][q]); v0 += oo.x; v1 += oo.y; }
+        d[u][q] = wbf(v0, v1);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const long long vu = vox + u * vstep;
+      if (vu < V) stg16(dxn + vu * lddx, make_uint4(d[u][0], d[u][1], d[u][2], d[u][3]));
+    }
+  }
+}
+
 // dgamma[c] = Σ_n sums[n][c][1], dbeta[c] = Σ_n sums[n][c][0]
 __global__ void gn_param_grad_kernel(const double* __restrict__ sums, int N, int C, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int accumulate) {
@@ -534,8 +842,22 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
   }();
   B3D_CHECK_CUDA(attr);
   cudaStream_t st = (cudaStream_t)stream;
-  if (relu) { gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }
-  else { gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps); ++g_b3d_launches; }
+#define RARGS (const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, beta, G, sums, V, C, eps
+  // B3D_GN_LEAN: bit 0 = lean apply, bit 1 = lean reduce (register-lean kernels, fixed-chunk shapes only)
+  static const int lean = getenv("B3D_GN_LEAN") ? atoi(getenv("B3D_GN_LEAN")) : 3;
+  if ((lean & 2) && (GN_THREADS % (C / 8)) == 0) {
+    static const cudaError_t attr2 = [] {
+      cudaError_t e = cudaFuncSetAttribute(gn_bwd_reduce_lean_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(gn_bwd_reduce_lean_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+    }();
+    B3D_CHECK_CUDA(attr2);
+    if (relu) gn_bwd_reduce_lean_kernel<true, 4><<<grid, GN_THREADS, smem, st>>>(RARGS);
+    else gn_bwd_reduce_lean_kernel<false, 4><<<grid, GN_THREADS, smem, st>>>(RARGS);
+  } else if (relu) gn_bwd_reduce_kernel<true><<<grid, GN_THREADS, smem, st>>>(RARGS);
+  else gn_bwd_reduce_kernel<false><<<grid, GN_THREADS, smem, st>>>(RARGS);
+  ++g_b3d_launches;
+#undef RARGS
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -550,9 +872,19 @@ int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ld
 #define LAUNCH(RL, AC)                                                                                               \
   gn_bwd_apply_kernel<RL, AC><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, \
                                                               beta, G, sums, (bf16*)dx, lddx, V, C, eps)
+#define LAUNCHL(RL, AC)                                                                                                  \
+  gn_bwd_apply_lean_kernel<RL, AC, 2><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, \
+                                                                      beta, G, sums, (bf16*)dx, lddx, V, C, eps)
+  static const int lean = getenv("B3D_GN_LEAN") ? atoi(getenv("B3D_GN_LEAN")) : 3;
+  if ((lean & 1) && (GN_THREADS % (C / 8)) == 0) {
+    if (relu) { if (accumulate) LAUNCHL(true, true); else LAUNCHL(true, false); }
+    else { if (accumulate) LAUNCHL(false, true); else LAUNCHL(false, false); }
+  } else
   if (relu) { if (accumulate) LAUNCH(true, true); else LAUNCH(true, false); }
   else { if (accumulate) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
+#undef LAUNCHL
+  ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
@@ -578,11 +910,17 @@ int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ld
   const dim3 grid_r(per_sample, N), grid_a(ew_blocks(V * C8, GN_THREADS * 2), N);
 #define DUAL_ARGS_R (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, (const bf16*)yb, ldyb, stats_b, G, sums_a, sums_b, V, C, eps
 #define DUAL_ARGS_A (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, sums_a, (const bf16*)yb, ldyb, stats_b, gamma_b, sums_b, G, (bf16*)dxa, lddxa, (bf16*)dxb, lddxb, V, C, eps
-  if (occ == 3) gn_bwd_dual_reduce_kernel<3><<<grid_r, GN_THREADS, smem_r, st>>>(DUAL_ARGS_R);
+  // B3D_GN_DUAL_LEAN: bit 0 = lean apply kernel, bit 1 = lean reduce kernel (see the kernels' header)
+  static const int lean = getenv("B3D_GN_DUAL_LEAN") ? atoi(getenv("B3D_GN_DUAL_LEAN")) : 3;
+  if (lean & 2) {
+    const dim3 grid_l(std::max(1, std::min(ew_blocks(V * C8, GN_THREADS * 8), b3d_num_sms() * 3 / std::max(1, N))), N);
+    gn_bwd_dual_reduce_lean_kernel<2><<<grid_l, GN_THREADS, smem_r, st>>>(DUAL_ARGS_R);
+  } else if (occ == 3) gn_bwd_dual_reduce_kernel<3><<<grid_r, GN_THREADS, smem_r, st>>>(DUAL_ARGS_R);
   else gn_bwd_dual_reduce_kernel<2><<<grid_r, GN_THREADS, smem_r, st>>>(DUAL_ARGS_R);
   ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
-  if (occ == 3) gn_bwd_dual_apply_kernel<3><<<grid_a, GN_THREADS, smem_a, st>>>(DUAL_ARGS_A);
+  if (lean & 1) gn_bwd_dual_apply_lean_kernel<2><<<grid_a, GN_THREADS, smem_a, st>>>(DUAL_ARGS_A);
+  else if (occ == 3) gn_bwd_dual_apply_kernel<3><<<grid_a, GN_THREADS, smem_a, st>>>(DUAL_ARGS_A);
   else gn_bwd_dual_apply_kernel<2><<<grid_a, GN_THREADS, smem_a, st>>>(DUAL_ARGS_A);
   ++g_b3d_launches;
 #undef DUAL_ARGS_R
