@@ -1,5 +1,5 @@
 """A few launches of each kernel whose `ncu --set full` capture is committed under profiles/ (one target per invocation):
-    python scripts/ncu_targets.py zs | pwadd | dsloss | adamw | gnbwd"""
+    python scripts/ncu_targets.py zs | pwadd | dsloss | adamw | gnbwd | deep"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -50,5 +50,13 @@ elif what == "gnbwd":   # dual GroupNorm backward @2x128^3x32
     sa, sb = stats(y2), stats(r)
     for _ in range(4):
         ops.gn_bwd_dual(dy, y2, sa, gam, bet, r, sb, gam, 8)
+elif what == "deep":    # weight-streaming deep-level conv: 3x3x3 1024 -> 512 @2x8^3 (ups.2 conv1), split-K igemm_kernel
+    x = torch.randn(2, 8, 8, 8, 1024, device=dev).to(bf)
+    w = torch.randn(512, 1024, 3, 3, 3, device=dev) * 0.01
+    wp, kp, rows = ops.pack_weight(w, ops.PACK_FPROP)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(4):
+        flush.zero_()                      # weights come from HBM, as inside a real step
+        ops.conv_fprop(x, wp, rows, 512, 3, groups=8)
 torch.cuda.synchronize()
 print("ok", what)

@@ -341,9 +341,21 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * FIN_CIB;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nci = min(FIN_CIB, Cin - ci0), nco = min(32, Cout - co0);
-  for (int r = w; r < nci * ntaps; r += 8) {
-    const int tap = r / nci, cil = r - tap * nci;   // consecutive rows of one tap are adjacent in dwacc
-    tile[cil][tap][lane] = (lane < nco) ? __ldcs(acc + ((long long)tap * Cin_pad + ci0 + cil) * Cout_pad + co0 + lane) : 0.f;
+  // nine independent 128-byte row loads in flight per warp (one at a time left the large gradients latency bound)
+  const int nrows = nci * ntaps;
+  for (int r0 = w; r0 < nrows; r0 += 8 * 9) {
+    float v[9];
+#pragma unroll
+    for (int u = 0; u < 9; ++u) {
+      const int r = r0 + 8 * u;
+      const int tap = r / nci, cil = r - tap * nci;   // consecutive rows of one tap are adjacent in dwacc
+      v[u] = (r < nrows && lane < nco) ? __ldcs(acc + ((long long)tap * Cin_pad + ci0 + cil) * Cout_pad + co0 + lane) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 9; ++u) {
+      const int r = r0 + 8 * u;
+      if (r < nrows) { const int tap = r / nci, cil = r - tap * nci; tile[cil][tap][lane] = v[u]; }
+    }
   }
   __syncthreads();
   if (mode == 0) {

@@ -393,14 +393,16 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
     // every lane owns ONE fixed 8-channel chunk.  Its 64 constants are re-read per voxel from shared memory as 16 float4
     // broadcasts (a chunk-major copy, instead of 64 scalar reads), two voxel groups are in flight, and the arithmetic keeps the
     // association of the generic path (the ReLU mask must agree with the forward's)
-    __shared__ __align__(16) float cst[32 * 64];   // [chunk][kind: mg rg gg mx rx gx sh wp][8]
+    // chunk stride 68 floats, not 64: lanes of different chunks would otherwise all hit the same four banks (an F/8-way
+    // conflict on every one of the 16 float4 reads per voxel — the 64^3 / 32^3 gates ran 3-8x over their byte share)
+    __shared__ __align__(16) float cst[32 * 68];   // [chunk][kind: mg rg gg mx rx gx sh wp][8] (+4 pad)
     for (int i = threadIdx.x; i < F8 * 64; i += blockDim.x) {
       const int c8 = i >> 6, kind = (i >> 3) & 7, j = i & 7, c = c8 * 8 + j;
-      cst[i] = kind == 0 ? mg[c] : kind == 1 ? rg[c] : kind == 2 ? gg[c] : kind == 3 ? mx[c] : kind == 4 ? rx[c]
+      cst[c8 * 68 + (i & 63)] = kind == 0 ? mg[c] : kind == 1 ? rg[c] : kind == 2 ? gg[c] : kind == 3 ? mx[c] : kind == 4 ? rx[c]
              : kind == 5 ? gx[c] : kind == 6 ? sh[c] : wp[c];
     }
     __syncthreads();
-    const float4* cl = reinterpret_cast<const float4*>(cst + (lc < F8 ? lc : 0) * 64);
+    const float4* cl = reinterpret_cast<const float4*>(cst + (lc < F8 ? lc : 0) * 68);
     constexpr int UP = 2;
     for (long long v0 = warp_id * vpw * UP; v0 < V; v0 += nwarps * vpw * UP) {
       uint4 ra[UP], rb[UP];
@@ -570,6 +572,7 @@ int b3d_gate_apply_bwd(const void* dout, long long lddo, const void* x, long lon
                        long long lddx, float* dpsin, double* dca, double* st_dpsi, int N, long long V, int C, float eps,
                        void* stream) {
   B3D_REQUIRE(C % 8 == 0 && (pow2(C / 8) || (C / 8) % 32 == 0) && C <= 4096, "gate_apply_bwd: C=%d unsupported", C);
+  // (fewer, longer CTAs at the small levels measured slower: 46.7 -> 77.3 us at 64^3 — the kernel wants thread-level parallelism)
   dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
   gate_apply_bwd_kernel<<<grid, 256, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const bf16*)dout, lddo, (const bf16*)x, ldx, psi_raw, st_psi, gpsi, bpsi_n, ca, (bf16*)dx, lddx, dpsin, dca, st_dpsi, V, C, eps); ++g_b3d_launches;
@@ -592,7 +595,8 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
                      void* dz, double* sums_g, double* sums_x, float* dwpsi, float* dbpsi, float* dgpsi, float* dbpsi_n,
                      int N, long long V, int F, float eps, void* stream) {
   B3D_REQUIRE(F % 8 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_bwd: F=%d unsupported", F);
-  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);   // (a single resident wave of long CTAs measured 30 % slower)
+  // (a single resident wave of long CTAs measured 30 % slower at level 0, and 2x slower at the 16^3 / 8^3 levels)
+  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
   static const cudaError_t attr = cudaFuncSetAttribute(gate_psi_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * (int)sizeof(float));   // one-time, thread-safe
   B3D_CHECK_CUDA(attr);
   gate_psi_bwd_kernel<<<grid, 256, 16 * F * sizeof(float), (cudaStream_t)stream>>>(

@@ -205,11 +205,18 @@ __global__ void __launch_bounds__(256, 2) ds_head_bwd_kernel(const float* __rest
       }
     }
   }
-  if (nchunks == 1 && lc < C8) {
+  const bool p2 = (lanes_c & (lanes_c - 1)) == 0;
+  if (nchunks == 1) {   // lanes lc, lc + lanes_c, ... of a warp own the same chunk: fold them with shuffles, then one shared atomic per warp
 #pragma unroll
     for (int k = 0; k < KCLS; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sdw[k * C + lc * 8 + j], gw[k][j]);
+      for (int j = 0; j < 8; ++j) gw[k][j] = p2 ? warp_sum_mod(gw[k][j], lanes_c) : gw[k][j];
+    if ((!p2 || lane < lanes_c) && lc < C8) {
+#pragma unroll
+      for (int k = 0; k < KCLS; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sdw[k * C + lc * 8 + j], gw[k][j]);
+    }
   }
   if (lc == 0) {
 #pragma unroll
@@ -513,7 +520,7 @@ static int ds_head_bwd_launch(const float* dl, bool channel_last, const void* x,
   B3D_REQUIRE(K == KCLS, "ds_head: only %d output classes supported (got %d)", KCLS, K);
   B3D_REQUIRE(C % 8 == 0 && C <= 2048, "ds_head: bad C");
   const size_t smem = (2 * KCLS * C + KCLS) * sizeof(float);
-  const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 6);
+  const int blocks = std::min(hd_blocks((long long)N * Vs * 8, 256), b3d_num_sms() * 2);   // one resident wave (128 registers: 2 CTAs per SM)
   cudaStream_t st = (cudaStream_t)stream;
 #define DSB(A, L) ds_head_bwd_kernel<A, L><<<blocks, 256, smem, st>>>(dl, (const bf16*)x, ldx, w, (bf16*)dx, lddx, dW, db, N, Vs, C)
   if (accumulate) { if (channel_last) DSB(true, true); else DSB(true, false); }

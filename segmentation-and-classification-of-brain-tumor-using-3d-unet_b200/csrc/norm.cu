@@ -25,6 +25,28 @@ __device__ __forceinline__ void gn_mean_rstd(const double* __restrict__ stats, i
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Group terms of the GroupNorm backward, block-cooperative: grp[2g], grp[2g+1] = Σ_{k in group g} γ_k · sums[n][k][0|1]
+// (fp64).  One warp per group, lanes strided over the group's channels.  The apply kernels used to run this sum serially
+// per channel in every block (C/G dependent fp64 loads deep: ~10 us of prologue at the 512-channel levels, where the whole
+// tensor is 1 MB).  Ends with a __syncthreads().  G <= GN_MAXG.
+#define GN_MAXG 32
+__device__ __forceinline__ void gn_group_terms(const float* __restrict__ gamma, const double* __restrict__ sums, int n, int C,
+                                               int G, double* grp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int cpg = C / G;
+  for (int g = warp; g < G; g += nw) {
+    double sb = 0, sc = 0;
+    for (int k = g * cpg + lane; k < (g + 1) * cpg; k += 32) {
+      const double ga = (double)gamma[k];
+      sb += ga * sums[((long long)n * C + k) * 2];
+      sc += ga * sums[((long long)n * C + k) * 2 + 1];
+    }
+    sb = warp_sum_d(sb); sc = warp_sum_d(sc);
+    if (lane == 0) { grp[2 * g] = sb; grp[2 * g + 1] = sc; }
+  }
+  __syncthreads();
+}
+
 // out = act(GN(y)) [+ GN_r(r) | + r]
 template <bool RELU, int RES>  // RES: 0 none, 1 GroupNorm'd residual, 2 plain residual
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(
@@ -224,15 +246,13 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(
   const int n = blockIdx.y;
   const int cpg = C / G;
   const double m = (double)cpg * (double)V;
+  __shared__ double s_grp[2 * GN_MAXG];
+  gn_group_terms(gamma, sums, n, C, G, s_grp);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     const int g = c / cpg;
     gn_mean_rstd(stats, n, G, g, m, eps, mean, rstd);
-    double sb = 0, sc2 = 0;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-      sb += (double)gamma[k] * sums[((long long)n * C + k) * 2];
-      sc2 += (double)gamma[k] * sums[((long long)n * C + k) * 2 + 1];
-    }
+    const double sb = s_grp[2 * g], sc2 = s_grp[2 * g + 1];
     s_mean[c] = mean; s_rstd[c] = rstd; s_g[c] = gamma[c]; s_b[c] = beta[c];
     s_B[c] = (float)(sb / m) * rstd; s_C[c] = (float)(sc2 / m) * rstd;
   }
@@ -394,24 +414,19 @@ __global__ void __launch_bounds__(GN_THREADS, OCC) gn_bwd_dual_apply_kernel(
   const int n = blockIdx.y;
   const int cpg = C / G;
   const double m = (double)cpg * (double)V;
+  __shared__ double s_grp[4 * GN_MAXG];
+  gn_group_terms(gamma_a, sums_a, n, C, G, s_grp);
+  gn_group_terms(gamma_b, sums_b, n, C, G, s_grp + 2 * GN_MAXG);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     float mean, rstd;
     gn_mean_rstd(stats_a, n, G, g, m, eps, mean, rstd);
-    double sb = 0, sc2 = 0;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-      sb += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2];
-      sc2 += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2 + 1];
-    }
+    double sb = s_grp[2 * g], sc2 = s_grp[2 * g + 1];
     float Bg = (float)(sb / m) * rstd, Cg = (float)(sc2 / m) * rstd, kb = -mean * rstd;
     { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }   // the forward's own expression
     c_Pa[c] = gamma_a[c] * rstd; c_Qa[c] = fmaf(kb, Cg, Bg); c_Ra[c] = rstd * Cg;
     gn_mean_rstd(stats_b, n, G, g, m, eps, mean, rstd);
-    sb = 0; sc2 = 0;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-      sb += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2];
-      sc2 += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2 + 1];
-    }
+    sb = s_grp[2 * GN_MAXG + 2 * g]; sc2 = s_grp[2 * GN_MAXG + 2 * g + 1];
     Bg = (float)(sb / m) * rstd; Cg = (float)(sc2 / m) * rstd; kb = -mean * rstd;
     c_Pb[c] = gamma_b[c] * rstd; c_Qb[c] = fmaf(kb, Cg, Bg); c_Rb[c] = rstd * Cg;
   }
@@ -465,6 +480,11 @@ __global__ void __launch_bounds__(GN_THREADS, OCC) gn_bwd_dual_apply_kernel(
 // the loop instead of living in 48-64 registers per thread: ~60 registers -> four resident blocks per SM instead of two,
 // i.e. twice the loads in flight for a kernel that is purely latency x bandwidth bound (ncu round 2: 126 registers, 25 % warps
 // active, 4.6 TB/s).  Arithmetic expressions are the same as in the kernels above (bit-identical results).
+// Coefficient layout: [kind][chunk][8 + 2 pad] floats — the lanes of a warp (different chunks) read 8-byte words 40 bytes
+// apart, which spreads 16 chunks over all 32 banks (a plain [kind][channel] layout is C/32-way conflicted: 16-way at C = 512).
+// GN_KS(C) = floats per kind.
+#define GN_KS(C) ((C) + ((C) >> 2))
+__device__ __forceinline__ int kidx(int kind, int c, int C) { return kind * GN_KS(C) + (c >> 3) * 10 + (c & 7); }
 
 template <int UB>
 __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_dual_apply_lean_kernel(
@@ -474,31 +494,26 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_dual_apply_lean_kernel(
     const double* __restrict__ sums_b, int G, bf16* __restrict__ dxa, long long lddxa, bf16* __restrict__ dxb, long long lddxb,
     long long V, int C, float eps) {
   extern __shared__ float sm[];
-  float* c_S = sm; float* c_T = sm + C; float* c_Pa = sm + 2 * C; float* c_Qa = sm + 3 * C; float* c_Ra = sm + 4 * C;
-  float* c_Pb = sm + 5 * C; float* c_Qb = sm + 6 * C; float* c_Rb = sm + 7 * C;
+  constexpr int c_S = 0; constexpr int c_T = 1; constexpr int c_Pa = 2; constexpr int c_Qa = 3; constexpr int c_Ra = 4;
+  constexpr int c_Pb = 5; constexpr int c_Qb = 6; constexpr int c_Rb = 7;
   const int n = blockIdx.y;
   const int cpg = C / G;
   const double m = (double)cpg * (double)V;
+  __shared__ double s_grp[4 * GN_MAXG];
+  gn_group_terms(gamma_a, sums_a, n, C, G, s_grp);
+  gn_group_terms(gamma_b, sums_b, n, C, G, s_grp + 2 * GN_MAXG);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     float mean, rstd;
     gn_mean_rstd(stats_a, n, G, g, m, eps, mean, rstd);
-    double sb = 0, sc2 = 0;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-      sb += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2];
-      sc2 += (double)gamma_a[k] * sums_a[((long long)n * C + k) * 2 + 1];
-    }
+    double sb = s_grp[2 * g], sc2 = s_grp[2 * g + 1];
     float Bg = (float)(sb / m) * rstd, Cg = (float)(sc2 / m) * rstd, kb = -mean * rstd;
-    { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }
-    c_Pa[c] = gamma_a[c] * rstd; c_Qa[c] = fmaf(kb, Cg, Bg); c_Ra[c] = rstd * Cg;
+    { const float sa = gamma_a[c] * rstd; sm[kidx(c_S, c, C)] = sa; sm[kidx(c_T, c, C)] = beta_a[c] - mean * sa; }
+    sm[kidx(c_Pa, c, C)] = gamma_a[c] * rstd; sm[kidx(c_Qa, c, C)] = fmaf(kb, Cg, Bg); sm[kidx(c_Ra, c, C)] = rstd * Cg;
     gn_mean_rstd(stats_b, n, G, g, m, eps, mean, rstd);
-    sb = 0; sc2 = 0;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-      sb += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2];
-      sc2 += (double)gamma_b[k] * sums_b[((long long)n * C + k) * 2 + 1];
-    }
+    sb = s_grp[2 * GN_MAXG + 2 * g]; sc2 = s_grp[2 * GN_MAXG + 2 * g + 1];
     Bg = (float)(sb / m) * rstd; Cg = (float)(sc2 / m) * rstd; kb = -mean * rstd;
-    c_Pb[c] = gamma_b[c] * rstd; c_Qb[c] = fmaf(kb, Cg, Bg); c_Rb[c] = rstd * Cg;
+    sm[kidx(c_Pb, c, C)] = gamma_b[c] * rstd; sm[kidx(c_Qb, c, C)] = fmaf(kb, Cg, Bg); sm[kidx(c_Rb, c, C)] = rstd * Cg;
   }
   __syncthreads();
   const int C8 = C >> 3;
@@ -508,7 +523,8 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_dual_apply_lean_kernel(
   const bf16* ybn = yb + (long long)n * V * ldyb + c0;
   bf16* dxan = dxa + (long long)n * V * lddxa + c0;
   bf16* dxbn = dxb + (long long)n * V * lddxb + c0;
-  const float* kc = sm + c0;
+  const float* kc = sm + (int)(threadIdx.x % C8) * 10;   // padded coefficient layout (kidx)
+  const int KS = GN_KS(C);
   const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
   long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
   for (; vox < V; vox += UB * vstep) {
@@ -523,9 +539,9 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_dual_apply_lean_kernel(
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 S = lds2v(kc + 2 * q), T = lds2v(kc + C + 2 * q), Pa = lds2v(kc + 2 * C + 2 * q),
-                   Qa = lds2v(kc + 3 * C + 2 * q), Ra = lds2v(kc + 4 * C + 2 * q), Pb = lds2v(kc + 5 * C + 2 * q),
-                   Qb = lds2v(kc + 6 * C + 2 * q), Rb = lds2v(kc + 7 * C + 2 * q);
+      const float2 S = lds2v(kc + 0 * KS + 2 * q), T = lds2v(kc + 1 * KS + 2 * q), Pa = lds2v(kc + 2 * KS + 2 * q),
+                   Qa = lds2v(kc + 3 * KS + 2 * q), Ra = lds2v(kc + 4 * KS + 2 * q), Pb = lds2v(kc + 5 * KS + 2 * q),
+                   Qb = lds2v(kc + 6 * KS + 2 * q), Rb = lds2v(kc + 7 * KS + 2 * q);
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]), zz = bfw(z[u][q]);
@@ -554,17 +570,17 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_dual_reduce_lean_kernel(
     const double* __restrict__ stats_b, int G, double* __restrict__ sums_a, double* __restrict__ sums_b, long long V, int C,
     float eps) {
   extern __shared__ float sm[];
-  float* c_ka = sm; float* c_kb = sm + C; float* c_S = sm + 2 * C; float* c_T = sm + 3 * C;
-  float* c_kab = sm + 4 * C; float* c_kbb = sm + 5 * C;
-  double* red = reinterpret_cast<double*>(sm + 6 * C);   // [4][C]: Σdz_a, Σdz_a·x̂a, Σdy, Σdy·x̂b
+  constexpr int c_ka = 0; constexpr int c_kb = 1; constexpr int c_S = 2; constexpr int c_T = 3;
+  constexpr int c_kab = 4; constexpr int c_kbb = 5;
+  double* red = reinterpret_cast<double*>(sm + 6 * GN_KS(C));   // [4][C]: Σdz_a, Σdz_a·x̂a, Σdy, Σdy·x̂b
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     gn_mean_rstd(stats_a, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
-    c_ka[c] = rstd; c_kb[c] = -mean * rstd;
-    { const float sa = gamma_a[c] * rstd; c_S[c] = sa; c_T[c] = beta_a[c] - mean * sa; }
+    sm[kidx(c_ka, c, C)] = rstd; sm[kidx(c_kb, c, C)] = -mean * rstd;
+    { const float sa = gamma_a[c] * rstd; sm[kidx(c_S, c, C)] = sa; sm[kidx(c_T, c, C)] = beta_a[c] - mean * sa; }
     gn_mean_rstd(stats_b, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
-    c_kab[c] = rstd; c_kbb[c] = -mean * rstd;
+    sm[kidx(c_kab, c, C)] = rstd; sm[kidx(c_kbb, c, C)] = -mean * rstd;
     red[c] = 0.0; red[C + c] = 0.0; red[2 * C + c] = 0.0; red[3 * C + c] = 0.0;
   }
   __syncthreads();
@@ -573,7 +589,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_dual_reduce_lean_kernel(
   const bf16* dyn = dy + (long long)n * V * lddy + c0;
   const bf16* yan = ya + (long long)n * V * ldya + c0;
   const bf16* ybn = yb + (long long)n * V * ldyb + c0;
-  const float* kc = sm + c0;
+  const float* kc = sm + (int)(threadIdx.x % C8) * 10;   // padded coefficient layout (kidx)
+  const int KS = GN_KS(C);
   float a1[8], a2[8], a3[8], a4[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; a4[j] = 0.f; }
@@ -594,8 +611,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_dual_reduce_lean_kernel(
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 ka = lds2v(kc + 2 * q), kb = lds2v(kc + C + 2 * q), S = lds2v(kc + 2 * C + 2 * q),
-                   T = lds2v(kc + 3 * C + 2 * q), kab = lds2v(kc + 4 * C + 2 * q), kbb = lds2v(kc + 5 * C + 2 * q);
+      const float2 ka = lds2v(kc + 0 * KS + 2 * q), kb = lds2v(kc + 1 * KS + 2 * q), S = lds2v(kc + 2 * KS + 2 * q),
+                   T = lds2v(kc + 3 * KS + 2 * q), kab = lds2v(kc + 4 * KS + 2 * q), kbb = lds2v(kc + 5 * KS + 2 * q);
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]), zz = bfw(z[u][q]);
@@ -638,13 +655,13 @@ __global__ void __launch_bounds__(GN_THREADS, UB >= 4 ? 3 : 4) gn_bwd_reduce_lea
     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
     double* __restrict__ sums, long long V, int C, float eps) {
   extern __shared__ float sm[];
-  float* c_ka = sm; float* c_kb = sm + C; float* c_kg = sm + 2 * C; float* c_kbe = sm + 3 * C;
-  double* red = reinterpret_cast<double*>(sm + 4 * C);
+  constexpr int c_ka = 0; constexpr int c_kb = 1; constexpr int c_kg = 2; constexpr int c_kbe = 3;
+  double* red = reinterpret_cast<double*>(sm + 4 * GN_KS(C));
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     gn_mean_rstd(stats, n, G, c / (C / G), (double)(C / G) * (double)V, eps, mean, rstd);
-    c_ka[c] = rstd; c_kb[c] = -mean * rstd; c_kg[c] = gamma[c]; c_kbe[c] = beta[c];
+    sm[kidx(c_ka, c, C)] = rstd; sm[kidx(c_kb, c, C)] = -mean * rstd; sm[kidx(c_kg, c, C)] = gamma[c]; sm[kidx(c_kbe, c, C)] = beta[c];
     red[c] = 0.0; red[C + c] = 0.0;
   }
   __syncthreads();
@@ -652,7 +669,8 @@ __global__ void __launch_bounds__(GN_THREADS, UB >= 4 ? 3 : 4) gn_bwd_reduce_lea
   const int c0 = (int)(threadIdx.x % C8) * 8;
   const bf16* dyn = dy + (long long)n * V * lddy + c0;
   const bf16* yn = y + (long long)n * V * ldy + c0;
-  const float* kc = sm + c0;
+  const float* kc = sm + (int)(threadIdx.x % C8) * 10;   // padded coefficient layout (kidx)
+  const int KS = GN_KS(C);
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
@@ -672,9 +690,9 @@ __global__ void __launch_bounds__(GN_THREADS, UB >= 4 ? 3 : 4) gn_bwd_reduce_lea
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 ka = lds2v(kc + 2 * q), kb = lds2v(kc + C + 2 * q);
+      const float2 ka = lds2v(kc + 0 * KS + 2 * q), kb = lds2v(kc + 1 * KS + 2 * q);
       float2 kg = make_float2(0.f, 0.f), kbe = kg;
-      if (RELU) { kg = lds2v(kc + 2 * C + 2 * q); kbe = lds2v(kc + 3 * C + 2 * q); }
+      if (RELU) { kg = lds2v(kc + 2 * KS + 2 * q); kbe = lds2v(kc + 3 * KS + 2 * q); }
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const float2 dd = bfw(d[u][q]), xx = bfw(x[u][q]);
@@ -707,22 +725,20 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_apply_lean_kernel(
     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int G,
     const double* __restrict__ sums, bf16* __restrict__ dx, long long lddx, long long V, int C, float eps) {
   extern __shared__ float sm[];
-  float* c_ka = sm; float* c_kb = sm + C; float* c_kg = sm + 2 * C; float* c_kbe = sm + 3 * C;
-  float* c_B = sm + 4 * C; float* c_C = sm + 5 * C;
+  constexpr int c_ka = 0; constexpr int c_kb = 1; constexpr int c_kg = 2; constexpr int c_kbe = 3;
+  constexpr int c_B = 4; constexpr int c_C = 5;
   const int n = blockIdx.y;
   const int cpg = C / G;
   const double m = (double)cpg * (double)V;
+  __shared__ double s_grp[2 * GN_MAXG];
+  gn_group_terms(gamma, sums, n, C, G, s_grp);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd;
     const int g = c / cpg;
     gn_mean_rstd(stats, n, G, g, m, eps, mean, rstd);
-    double sb = 0, sc2 = 0;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) {
-      sb += (double)gamma[k] * sums[((long long)n * C + k) * 2];
-      sc2 += (double)gamma[k] * sums[((long long)n * C + k) * 2 + 1];
-    }
-    c_ka[c] = rstd; c_kb[c] = -mean * rstd; c_kg[c] = gamma[c]; c_kbe[c] = beta[c];
-    c_B[c] = (float)(sb / m) * rstd; c_C[c] = (float)(sc2 / m) * rstd;
+    const double sb = s_grp[2 * g], sc2 = s_grp[2 * g + 1];
+    sm[kidx(c_ka, c, C)] = rstd; sm[kidx(c_kb, c, C)] = -mean * rstd; sm[kidx(c_kg, c, C)] = gamma[c]; sm[kidx(c_kbe, c, C)] = beta[c];
+    sm[kidx(c_B, c, C)] = (float)(sb / m) * rstd; sm[kidx(c_C, c, C)] = (float)(sc2 / m) * rstd;
   }
   __syncthreads();
   const int C8 = C >> 3;
@@ -730,7 +746,8 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_apply_lean_kernel(
   const bf16* dyn = dy + (long long)n * V * lddy + c0;
   const bf16* yn = y + (long long)n * V * ldy + c0;
   bf16* dxn = dx + (long long)n * V * lddx + c0;
-  const float* kc = sm + c0;
+  const float* kc = sm + (int)(threadIdx.x % C8) * 10;   // padded coefficient layout (kidx)
+  const int KS = GN_KS(C);
   const long long vstep = ((long long)gridDim.x * blockDim.x) / C8;
   long long vox = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / C8;
   for (; vox < V; vox += UB * vstep) {
@@ -745,8 +762,8 @@ __global__ void __launch_bounds__(GN_THREADS, 4) gn_bwd_apply_lean_kernel(
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 ka = lds2v(kc + 2 * q), kb = lds2v(kc + C + 2 * q), kg = lds2v(kc + 2 * C + 2 * q),
-                   kbe = lds2v(kc + 3 * C + 2 * q), kB = lds2v(kc + 4 * C + 2 * q), kC = lds2v(kc + 5 * C + 2 * q);
+      const float2 ka = lds2v(kc + 0 * KS + 2 * q), kb = lds2v(kc + 1 * KS + 2 * q), kg = lds2v(kc + 2 * KS + 2 * q),
+                   kbe = lds2v(kc + 3 * KS + 2 * q), kB = lds2v(kc + 4 * KS + 2 * q), kC = lds2v(kc + 5 * KS + 2 * q);
       const float kA0 = kg.x * ka.x, kA1 = kg.y * ka.y;
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
@@ -834,11 +851,11 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
   // exactly one resident wave (3 CTAs per SM): 4 per SM ran 1.33 waves, the last one a third full
   const int per_sample = std::max(1, std::min(ew_blocks(V * (C / 8), GN_THREADS * 8), b3d_num_sms() * 3 / std::max(1, N)));
   dim3 grid(per_sample, N);
-  const size_t smem = 8 * (size_t)C * sizeof(float);   // 4C floats + 2C doubles
+  const size_t smem = (4 * (size_t)GN_KS(C) + 4 * (size_t)C) * sizeof(float);   // 4 padded coefficient arrays + 2C doubles
   static const cudaError_t attr = [] {   // one-time, thread-safe; up to 64 KB at C = GN_MAXC (the wide model's 2048-channel concat buffers)
-    cudaError_t e = cudaFuncSetAttribute(gn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(gn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * GN_MAXC * (int)sizeof(float));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+    return cudaFuncSetAttribute(gn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * GN_MAXC * (int)sizeof(float));
   }();
   B3D_CHECK_CUDA(attr);
   cudaStream_t st = (cudaStream_t)stream;
@@ -847,9 +864,9 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
   static const int lean = getenv("B3D_GN_LEAN") ? atoi(getenv("B3D_GN_LEAN")) : 3;
   if ((lean & 2) && (GN_THREADS % (C / 8)) == 0) {
     static const cudaError_t attr2 = [] {
-      cudaError_t e = cudaFuncSetAttribute(gn_bwd_reduce_lean_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+      cudaError_t e = cudaFuncSetAttribute(gn_bwd_reduce_lean_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * GN_MAXC * (int)sizeof(float));
       if (e != cudaSuccess) return e;
-      return cudaFuncSetAttribute(gn_bwd_reduce_lean_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * GN_MAXC * (int)sizeof(float));
+      return cudaFuncSetAttribute(gn_bwd_reduce_lean_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * GN_MAXC * (int)sizeof(float));
     }();
     B3D_CHECK_CUDA(attr2);
     if (relu) gn_bwd_reduce_lean_kernel<true, 4><<<grid, GN_THREADS, smem, st>>>(RARGS);
@@ -865,9 +882,9 @@ int b3d_gn_bwd_reduce(const void* dy, long long lddy, const void* y, long long l
 int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ldy, const double* stats,
                      const float* gamma, const float* beta, int G, int relu, const double* sums, void* dx,
                      long long lddx, int accumulate, int N, long long V, int C, float eps, void* stream) {
-  B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0, "gn_bwd_apply: bad C=%d G=%d", C, G);
+  B3D_REQUIRE(C % 8 == 0 && C <= GN_MAXC && C % G == 0 && G <= GN_MAXG, "gn_bwd_apply: bad C=%d G=%d", C, G);
   dim3 grid(ew_blocks(V * (C / 8), GN_THREADS * 2), N);
-  const size_t smem = 6 * (size_t)C * sizeof(float);
+  const size_t smem = 6 * (size_t)GN_KS(C) * sizeof(float);   // six (padded, see kidx) coefficient arrays
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(RL, AC)                                                                                               \
   gn_bwd_apply_kernel<RL, AC><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, \
@@ -876,6 +893,18 @@ int b3d_gn_bwd_apply(const void* dy, long long lddy, const void* y, long long ld
   gn_bwd_apply_lean_kernel<RL, AC, 2><<<grid, GN_THREADS, smem, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, stats, gamma, \
                                                                       beta, G, sums, (bf16*)dx, lddx, V, C, eps)
   static const int lean = getenv("B3D_GN_LEAN") ? atoi(getenv("B3D_GN_LEAN")) : 3;
+  static const cudaError_t attr = [] {   // 48 KB of coefficients at C = 2048 plus the static group-term scratch: opt in once
+    const int mx = 6 * GN_KS(GN_MAXC) * (int)sizeof(float);
+    cudaError_t e = cudaSuccess;
+#define SETA(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)
+    SETA((gn_bwd_apply_kernel<true, true>)); SETA((gn_bwd_apply_kernel<true, false>));
+    SETA((gn_bwd_apply_kernel<false, true>)); SETA((gn_bwd_apply_kernel<false, false>));
+    SETA((gn_bwd_apply_lean_kernel<true, true, 2>)); SETA((gn_bwd_apply_lean_kernel<true, false, 2>));
+    SETA((gn_bwd_apply_lean_kernel<false, true, 2>)); SETA((gn_bwd_apply_lean_kernel<false, false, 2>));
+#undef SETA
+    return e;
+  }();
+  B3D_CHECK_CUDA(attr);
   if ((lean & 1) && (GN_THREADS % (C / 8)) == 0) {
     if (relu) { if (accumulate) LAUNCHL(true, true); else LAUNCHL(true, false); }
     else { if (accumulate) LAUNCHL(false, true); else LAUNCHL(false, false); }
@@ -896,7 +925,7 @@ int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ld
                     const float* gamma_a, const float* beta_a, const void* yb, long long ldyb, const double* stats_b,
                     const float* gamma_b, int G, double* sums_a, double* sums_b, void* dxa, long long lddxa, void* dxb,
                     long long lddxb, int N, long long V, int C, float eps, void* stream) {
-  B3D_REQUIRE(C % 8 == 0 && C % G == 0, "gn_bwd_dual: bad C=%d G=%d", C, G);
+  B3D_REQUIRE(C % 8 == 0 && C % G == 0 && G <= GN_MAXG, "gn_bwd_dual: bad C=%d G=%d", C, G);
   const int C8 = C / 8;
   if (C > 512 || (GN_THREADS % C8) != 0) return 1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -906,7 +935,7 @@ int b3d_gn_bwd_dual(const void* dy, long long lddy, const void* ya, long long ld
   // 2x128^3x32 (scripts/gn_dual_once.py): OCC 2 0.485 ms, OCC 3 0.635 ms — the spills cost more than the extra warps hide,
   // so 2 is the default; B3D_GN_DUAL_OCC=3 keeps the experiment reproducible.
   static const int occ = getenv("B3D_GN_DUAL_OCC") ? atoi(getenv("B3D_GN_DUAL_OCC")) : 2;
-  const size_t smem_r = (6 * (size_t)C) * sizeof(float) + 4 * (size_t)C * sizeof(double), smem_a = 8 * (size_t)C * sizeof(float);
+  const size_t smem_r = (6 * (size_t)GN_KS(C)) * sizeof(float) + 4 * (size_t)C * sizeof(double), smem_a = 8 * (size_t)GN_KS(C) * sizeof(float);
   const dim3 grid_r(per_sample, N), grid_a(ew_blocks(V * C8, GN_THREADS * 2), N);
 #define DUAL_ARGS_R (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, (const bf16*)yb, ldyb, stats_b, G, sums_a, sums_b, V, C, eps
 #define DUAL_ARGS_A (const bf16*)dy, lddy, (const bf16*)ya, ldya, stats_a, gamma_a, beta_a, sums_a, (const bf16*)yb, ldyb, stats_b, gamma_b, sums_b, G, (bf16*)dxa, lddxa, (bf16*)dxb, lddxb, V, C, eps
