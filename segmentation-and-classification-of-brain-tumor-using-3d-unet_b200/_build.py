@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libb3d.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math",
-]
+] + os.environ.get("B3D_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DB3D_STG_CS for a tuning build (changes the stamp: full rebuild)
 
 
 def _sources():

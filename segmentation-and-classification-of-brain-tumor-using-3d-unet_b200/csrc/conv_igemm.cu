@@ -17,11 +17,11 @@
 //   * weights: ONE TMA box per step from the packed [(kh,kw)][kd][Cout][K] tensor (the 9 (kh,kw) taps of this kd).
 //   * accumulators live in TMEM (MB x BN fp32 columns, double-buffered when they fit); the MMA loop is templated on
 //     (BN, KC) and unrolled so the single issuing thread spends a few uniform-datapath instructions per tcgen05.mma
-//     (scripts/umma_rate.cu: a naive loop costs ~300 clk per MMA, the MMA itself 40-128); 4 epilogue warps drain TMEM,
+//     (scripts/umma_rate.cu: a naive loop costs ~300 clk per MMA, the MMA itself 40-128); 4 (8 for BN <= 32) epilogue warps drain TMEM,
 //     add bias, emit bf16 NDHWC with 32-byte stores (or fp32 split-K atomics, or the ConvTranspose pixel-shuffle scatter)
 //     and accumulate the GroupNorm / BatchNorm sum / sum-of-squares in registers (flushed once per sample / channel block).
 //   * persistent CTAs (one per SM), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-//     warps 2-5 = epilogue.
+//     warps 2-5 (2-9 for BN <= 32) = epilogue.
 //   * 3x3x3 layers with <= 64 output channels take the z-marching kd-stacked kernel in conv_zs.cu instead.
 #include "b3d_common.cuh"
 #include "b3d_internal.h"
@@ -30,7 +30,10 @@
 #include <math.h>
 #include <type_traits>
 
-#define IG_THREADS 192
+// producer warp, MMA warp, then 4 epilogue warps — or 8 (two per TMEM lane quadrant) for the narrow n-blocks of the streaming
+// launches (BN <= 32: no spills under the 168-register cap of a 320-thread CTA; BN >= 64 would spill up to 596 bytes)
+#define IG_EPI_WARPS(BN) ((BN) <= 32 ? 8 : 4)
+#define IG_THREADS(BN) (64 + 32 * IG_EPI_WARPS(BN))
 #define IG_MAXMB 32
 #define IG_MAXSTAGES 8
 
@@ -63,7 +66,7 @@ __device__ __forceinline__ void stg32(void* p, const uint4& a, const uint4& b) {
 
 // BN: output columns per item (UMMA N) ; KC: channels per pipeline step (smem row = KC*2 bytes = swizzle span)
 template <int BN, int KC>
-__global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_constant__ IgParams P) {
+__global__ void __launch_bounds__(IG_THREADS(BN), 1) igemm_kernel(const __grid_constant__ IgParams P) {
   constexpr int RB = KC * 2;
   constexpr int NK16 = KC / 16;
   constexpr uint32_t rb16 = RB / 16;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
   if (threadIdx.x == 0) {
     if (sA & 1023u) { if (P.err) atomicExch(P.err, 9); __trap(); }
     for (int i = 0; i < S; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, IG_EPI_WARPS(BN)); }
     mbar_fence_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 128) s_stats[threadIdx.x - 64] = 0.0;
@@ -186,10 +189,15 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       __syncwarp();
     }
   } else {
-    // ======================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =======================
+    // ======================= epilogue (warps 2..9 -> TMEM lane quadrants 2,3,0,1,2,3,0,1) =======================
+    // Two warps per lane quadrant, taking alternate M-blocks of the item: the drain of one M-block is a serial
+    // tcgen05.ld -> convert -> store chain, and four warps could not keep the streaming (1x1x1, ConvTranspose) launches fed
+    // (they ran at ~50 % of the HBM floor with the planner already on the best plan: scripts/pw_sweep.py, round 2).
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int MB_STEP = IG_EPI_WARPS(BN) / 4;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int et = threadIdx.x - 64;  // 0 .. 32 * IG_EPI_WARPS - 1
     const int plane = P.BH * P.BW;
     const int cpg = P.cpg;
     // statistics granule (channels per per-thread accumulator): 16, 4 or 1 — the host guarantees BN / granule <= 16
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         }
         a1[i] = 0.f; a2[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" :: "n"(32 * IG_EPI_WARPS(BN)) : "memory");
       const int groups_blk = (cur_n0 + BN - 1) / cpg - cur_n0 / cpg + 1;
       if (et < 2 * groups_blk) {
         const int g = cur_n0 / cpg + (et >> 1);
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
         }
         s_stats[et] = 0.0;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" :: "n"(32 * IG_EPI_WARPS(BN)) : "memory");
     };
     int it = 0;
     for (int item = blockIdx.x; item < P.num_items; item += gridDim.x, ++it) {
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_kernel(const __grid_const
       auto body = [&](auto MODE_c, auto GRAN_c, auto FULL_c) {
         constexpr int MODE = decltype(MODE_c)::value, GRAN = decltype(GRAN_c)::value;
         constexpr bool FULL = decltype(FULL_c)::value;
-        for (int mb = 0; mb < P.MB; ++mb) {
+        for (int mb = half; mb < P.MB; mb += MB_STEP) {
           const int p = P.mb_base[mb] + (row >> 3) * P.GS + (row & 7);
           const int pz = p / plane, pr = p - pz * plane;
           const int py = pr / P.BW, px = pr - py * P.BW;
@@ -581,7 +589,7 @@ template <int BN, int KC>
 static int ig_launch(const IgParams& P, size_t smem, int grid, cudaStream_t stream) {
   static const cudaError_t attr = cudaFuncSetAttribute(igemm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // one-time, thread-safe
   B3D_CHECK_CUDA(attr);
-  igemm_kernel<BN, KC><<<grid, IG_THREADS, smem, stream>>>(P); ++g_b3d_launches;
+  igemm_kernel<BN, KC><<<grid, IG_THREADS(BN), smem, stream>>>(P); ++g_b3d_launches;
   B3D_CHECK_CUDA(cudaGetLastError());
   return B3D_OK;
 }
