@@ -22,6 +22,13 @@ import torch
 from . import functional, ops
 
 
+def _capture_stream():
+    """The capture stream of the main chain.  B3D_MAIN_PRIORITY=-1 makes its kernel nodes outrank the weight-gradient side
+    stream (ops.WGRAD_STREAM, priority 0) when both have blocks pending (tuning knob; default 0 = equal priority)."""
+    import os
+    return torch.cuda.Stream(priority=int(os.environ.get("B3D_MAIN_PRIORITY", "0")))
+
+
 class GraphedTrainStep:
     def __init__(self, model, criterion, optimizer, example_x, example_y, warmup=3):
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
@@ -50,7 +57,7 @@ class GraphedTrainStep:
         self.optimizer.zero_grad(set_to_none=True)
         # thread_local: CUDA calls of other host threads (e.g. the NCCL watchdog polling events) must not invalidate the capture
         ops.reset_scratch()   # the capture must zero-fill its own scratch arenas (and nothing eager may slice them later)
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph, stream=_capture_stream(), capture_error_mode="thread_local"):
             self.loss = self._eager()
         ops.reset_scratch()
         torch.cuda.synchronize()
