@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(512) gate_se_bwd_kernel(const double* __restri
 // backward 2: dψr = GN1-backward(dψn) ; dz[c] = dψr * wψ[c] * [q_c>0]  (bf16 [N][V][F]) ;
 //   sums_g[n][c] += (Σdz, Σdz*x̂g) ; sums_x[n][c] += (Σdz, Σdz*x̂x) ; dwψ[c] += Σ dψr*q_c ; dbψ += Σ dψr
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
+__global__ void __launch_bounds__(256, 2) gate_psi_bwd_kernel(
     const float* __restrict__ dpsin, const float* __restrict__ psi_raw, const double* __restrict__ st_psi,
     const double* __restrict__ st_dpsi, const float* __restrict__ gpsi, const bf16* __restrict__ g1r,
     const bf16* __restrict__ x1r, const double* __restrict__ st_g, const double* __restrict__ st_x,
@@ -402,48 +402,56 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_kernel(
              : kind == 5 ? gx[c] : kind == 6 ? sh[c] : wp[c];
     }
     __syncthreads();
-    const float4* cl = reinterpret_cast<const float4*>(cst + (lc < F8 ? lc : 0) * 68);
-    constexpr int UP = 2;
+    const float* cb = cst + (lc < F8 ? lc : 0) * 68;
+    // four voxel groups in flight; the 64 constants of the lane's chunk are re-read two channels at a time (volatile 8-byte
+    // loads) so that they never occupy more than 16 registers: 2 CTAs per SM with 8 x 16-byte loads per thread in flight
+    constexpr int UP = 4;
     for (long long v0 = warp_id * vpw * UP; v0 < V; v0 += nwarps * vpw * UP) {
-      uint4 ra[UP], rb[UP];
+      unsigned wa[UP][4], wb[UP][4];
       float prv[UP], dpv[UP];
 #pragma unroll
       for (int u = 0; u < UP; ++u) {
         const long long v = v0 + u * vpw + lv;
         const bool ok = v < V && lc < F8;
-        ra[u] = ok ? ldg16_stream(gn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
-        rb[u] = ok ? ldg16_stream(xn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 ra = ok ? ldg16_stream(gn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 rb = ok ? ldg16_stream(xn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        wa[u][0] = ra.x; wa[u][1] = ra.y; wa[u][2] = ra.z; wa[u][3] = ra.w;
+        wb[u][0] = rb.x; wb[u][1] = rb.y; wb[u][2] = rb.z; wb[u][3] = rb.w;
         prv[u] = ok ? __ldg(psi_raw + (long long)n * V + v) : 0.f;
         dpv[u] = ok ? __ldg(dpsin + (long long)n * V + v) : 0.f;
+      }
+      float dpr[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        const bool ok = v < V && lc < F8;
+        const float xh = (prv[u] - mu) * rstd;
+        dpr[u] = ok ? rstd * (gp * dpv[u] - m1p - xh * m2p) : 0.f;   // 0: an absent voxel adds nothing to any sum
+        if (lc == 0) db += dpr[u];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 kmg = lds2v(cb + 0 * 8 + 2 * q), krg = lds2v(cb + 1 * 8 + 2 * q), kgg = lds2v(cb + 2 * 8 + 2 * q),
+                     kmx = lds2v(cb + 3 * 8 + 2 * q), krx = lds2v(cb + 4 * 8 + 2 * q), kgx = lds2v(cb + 5 * 8 + 2 * q),
+                     ksh = lds2v(cb + 6 * 8 + 2 * q), kwp = lds2v(cb + 7 * 8 + 2 * q);
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+          const float2 a = bfw(wa[u][q]), b = bfw(wb[u][q]);
+          const float xg0 = (a.x - kmg.x) * krg.x, xx0 = (b.x - kmx.x) * krx.x;
+          const float xg1 = (a.y - kmg.y) * krg.y, xx1 = (b.y - kmx.y) * krx.y;
+          const float q0 = fmaf(xg0, kgg.x, fmaf(xx0, kgx.x, ksh.x)), q1 = fmaf(xg1, kgg.y, fmaf(xx1, kgx.y, ksh.y));
+          const float dz0 = q0 > 0.f ? dpr[u] * kwp.x : 0.f, dz1 = q1 > 0.f ? dpr[u] * kwp.y : 0.f;
+          wa[u][q] = wbf(dz0, dz1);
+          a0[2 * q] += dz0; a1[2 * q] = fmaf(dz0, xg0, a1[2 * q]); a2[2 * q] = fmaf(dz0, xx0, a2[2 * q]);
+          a3[2 * q] = fmaf(dpr[u], fmaxf(q0, 0.f), a3[2 * q]);
+          a0[2 * q + 1] += dz1; a1[2 * q + 1] = fmaf(dz1, xg1, a1[2 * q + 1]); a2[2 * q + 1] = fmaf(dz1, xx1, a2[2 * q + 1]);
+          a3[2 * q + 1] = fmaf(dpr[u], fmaxf(q1, 0.f), a3[2 * q + 1]);
+        }
       }
 #pragma unroll
       for (int u = 0; u < UP; ++u) {
         const long long v = v0 + u * vpw + lv;
-        if (!(v < V && lc < F8)) continue;
-        const float xh = (prv[u] - mu) * rstd;
-        const float dpr = rstd * (gp * dpv[u] - m1p - xh * m2p);
-        if (lc == 0) db += dpr;
-        float a[8], b[8], o[8];
-        unpack8(ra[u], a); unpack8(rb[u], b);
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const float4 kmg = cl[0 + hf], krg = cl[2 + hf], kgg = cl[4 + hf], kmx = cl[6 + hf], krx = cl[8 + hf], kgx = cl[10 + hf],
-                       ksh = cl[12 + hf], kwp = cl[14 + hf];
-          const float vmg[4] = {kmg.x, kmg.y, kmg.z, kmg.w}, vrg[4] = {krg.x, krg.y, krg.z, krg.w}, vgg[4] = {kgg.x, kgg.y, kgg.z, kgg.w};
-          const float vmx[4] = {kmx.x, kmx.y, kmx.z, kmx.w}, vrx[4] = {krx.x, krx.y, krx.z, krx.w}, vgx[4] = {kgx.x, kgx.y, kgx.z, kgx.w};
-          const float vsh[4] = {ksh.x, ksh.y, ksh.z, ksh.w}, vwp[4] = {kwp.x, kwp.y, kwp.z, kwp.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = hf * 4 + jj;
-            const float xg = (a[j] - vmg[jj]) * vrg[jj], xx = (b[j] - vmx[jj]) * vrx[jj];
-            const float q = fmaf(xg, vgg[jj], fmaf(xx, vgx[jj], vsh[jj]));
-            const float dzv = q > 0.f ? dpr * vwp[jj] : 0.f;
-            o[j] = dzv;
-            const float qq = fmaxf(q, 0.f);
-            a0[j] += dzv; a1[j] = fmaf(dzv, xg, a1[j]); a2[j] = fmaf(dzv, xx, a2[j]); a3[j] = fmaf(dpr, qq, a3[j]);
-          }
-        }
-        stg16(dzn + v * F + lc * 8, pack8(o));
+        if (v < V && lc < F8) stg16(dzn + v * F + lc * 8, make_uint4(wa[u][0], wa[u][1], wa[u][2], wa[u][3]));
       }
     }
   } else

@@ -21,7 +21,7 @@ static int hd_blocks(long long total, int threads) {
 // deep-supervision 1x1 head: l[n][v][k] = b[k] + Σ_c skip[n][v][c] * W[k][c]      (fp32 float4 per voxel)
 // lanes of a warp = (voxel sub-index, 8-channel chunk); partial dots are reduced with shuffles.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ds_head_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 4) ds_head_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
                                                           const float* __restrict__ b, float4* __restrict__ out,
                                                           long long NV, int C) {
   extern __shared__ float sw[];  // [K][C]
