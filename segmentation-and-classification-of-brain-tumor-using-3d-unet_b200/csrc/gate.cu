@@ -57,6 +57,57 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
   const bf16* gn_ = g1r + (long long)n * V * F;
   const bf16* xn_ = x1r + (long long)n * V * F;
   float s1 = 0.f, s2 = 0.f;
+  if (F8 <= 32) {
+    // every lane owns one fixed 8-channel chunk: four voxel groups in flight, the chunk's 32 constants re-read two channels at
+    // a time from a padded shared tile (36-float chunk stride: lanes of different chunks hit different banks)
+    __shared__ __align__(16) float cst[32 * 36];   // [chunk][kind: scg scx sh wp][8] (+4 pad)
+    for (int i = threadIdx.x; i < F8 * 32; i += blockDim.x) {
+      const int c8 = i >> 5, kind = (i >> 3) & 3, j = i & 7, c = c8 * 8 + j;
+      cst[c8 * 36 + (i & 31)] = kind == 0 ? scg[c] : kind == 1 ? scx[c] : kind == 2 ? sh[c] : wp[c];
+    }
+    __syncthreads();
+    const float* cb = cst + (lc < F8 ? lc : 0) * 36;
+    constexpr int UP = 4;
+    for (long long v0 = warp_id * vpw * UP; v0 < V; v0 += nwarps * vpw * UP) {
+      unsigned wa[UP][4], wb[UP][4];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        const bool ok = v < V && lc < F8;
+        const uint4 ra = ok ? ldg16_stream(gn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        const uint4 rb = ok ? ldg16_stream(xn_ + v * F + lc * 8) : make_uint4(0u, 0u, 0u, 0u);
+        wa[u][0] = ra.x; wa[u][1] = ra.y; wa[u][2] = ra.z; wa[u][3] = ra.w;
+        wb[u][0] = rb.x; wb[u][1] = rb.y; wb[u][2] = rb.z; wb[u][3] = rb.w;
+      }
+      float acc[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) acc[u] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 kg = lds2v(cb + 0 * 8 + 2 * q), kx = lds2v(cb + 1 * 8 + 2 * q), ks = lds2v(cb + 2 * 8 + 2 * q),
+                     kw = lds2v(cb + 3 * 8 + 2 * q);
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+          const float2 a = bfw(wa[u][q]), b = bfw(wb[u][q]);
+          const float q0 = fmaxf(fmaf(a.x, kg.x, fmaf(b.x, kx.x, ks.x)), 0.f);
+          const float q1 = fmaxf(fmaf(a.y, kg.y, fmaf(b.y, kx.y, ks.y)), 0.f);
+          acc[u] = fmaf(q0, kw.x, acc[u]);      // same channel order as the generic path below
+          acc[u] = fmaf(q1, kw.y, acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const long long v = v0 + u * vpw + lv;
+        float t = (v < V && lc < F8) ? acc[u] : 0.f;
+        for (int o = lanes_c >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lc == 0 && v < V) {
+          const float p = t + bp;
+          psi_raw[(long long)n * V + v] = p;
+          s1 += p; s2 += p * p;
+        }
+      }
+    }
+  } else
   for (long long v0 = warp_id * vpw; v0 < V; v0 += nwarps * vpw) {
     const long long v = v0 + lv;
     float acc = 0.f;
