@@ -654,8 +654,12 @@ int b3d_gate_psi_bwd(const float* dpsin, const float* psi_raw, const double* st_
                      void* dz, double* sums_g, double* sums_x, float* dwpsi, float* dbpsi, float* dgpsi, float* dbpsi_n,
                      int N, long long V, int F, float eps, void* stream) {
   B3D_REQUIRE(F % 8 == 0 && (pow2(F / 8) || (F / 8) % 32 == 0) && F <= 1024, "gate_psi_bwd: F=%d unsupported", F);
-  // (a single resident wave of long CTAs measured 30 % slower at level 0, and 2x slower at the 16^3 / 8^3 levels)
-  dim3 grid(gt_blocks_per_sample(V * 8, 256, N), N);
+  // >= 2 iterations per warp (a warp iteration covers 4 groups of 32 / min(F/8, 32) voxels), capped at 8 CTAs per SM: every CTA
+  // ends with 4F fp64 atomics on the same addresses, which dominated the 32^3 level (50 us for a 14 us byte share) when all
+  // 592 CTAs per sample were launched for 2048 warp iterations.  (Level 0 reaches the cap; a single resident wave of long CTAs
+  // measured 30 % slower there.)
+  const int vpw_h = 32 / std::min(F / 8, 32);
+  dim3 grid(gt_blocks_per_sample(V, 256 / 32 * vpw_h * 4 * 2, N), N);
   static const cudaError_t attr = cudaFuncSetAttribute(gate_psi_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * (int)sizeof(float));   // one-time, thread-safe
   B3D_CHECK_CUDA(attr);
   gate_psi_bwd_kernel<<<grid, 256, 16 * F * sizeof(float), (cudaStream_t)stream>>>(
