@@ -239,6 +239,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Data parallel: SMs left to NCCL's channel CTAs (and NCCL_MAX_CTAS capped to the same number) so an all-reduce running beside
+# backward does not stall the persistent one-CTA-per-SM conv grids; 0 = off.  See DESIGN.md section 6.
+DP_RESERVED_SMS = "0"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,10 +280,15 @@ def main():
     os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dp_reserved = int(os.environ.get("B3D_DP_RESERVED_SMS", DP_RESERVED_SMS)) if world > 1 else 0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if dp_reserved > 0:   # NCCL's channel CTAs get their own SMs (read by NCCL when the communicator is created)
+            os.environ.setdefault("NCCL_MAX_CTAS", str(dp_reserved))
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
+    if dp_reserved > 0:
+        _lib.set_reserved_sms(dp_reserved)
     lib.b3d_launch_count.restype = ctypes.c_longlong
 
     torch.manual_seed(0)

@@ -30,6 +30,12 @@ long long b3d_launch_count(void);                    /* kernels launched by this
  * gradients bit-reproducible run to run, ~2 % slower per step.  1: one issuing warp without the scout (~13 % slower; kept for
  * comparison).  Default from env B3D_ORDERED_ISSUE.  Returns the previous mode.  Process-wide, atomic. */
 int b3d_set_ordered_issue(int on);
+/* Leave n SMs free in every grid this library launches from now on (all grids are sized from the SM count; the tensor-core
+ * kernels are persistent one-CTA-per-SM grids).  For data-parallel training (training.py:290-304 under one process per GPU):
+ * NCCL's channel CTAs cannot share an SM with a conv CTA, so a full-width conv grid launched while an all-reduce is running
+ * waits for the collective; with n = NCCL_MAX_CTAS reserved both run side by side.  Default from env B3D_RESERVED_SMS (0).
+ * Returns the previous reservation.  Process-wide, atomic; grids already captured into a CUDA graph keep their size. */
+int b3d_set_reserved_sms(int n);
 
 /* ---- convolutions on tcgen05 tensor cores (conv_igemm.cu, conv_wgrad.cu) ----------------------------------- */
 /* weight repack fp32 reference layout -> bf16 [K/8][taps][rows][8].

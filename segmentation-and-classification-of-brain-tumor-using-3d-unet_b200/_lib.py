@@ -73,3 +73,9 @@ def set_ordered_issue(on):
     issuers, whose accumulation order jitters by an fp32 ulp from run to run.  0 / False: two issuers; 1 / True: one issuer;
     2: one issuer fed by a scout warp that does the barrier waits and descriptor arithmetic.  Returns the previous mode."""
     return int(lib().b3d_set_ordered_issue(c_int(int(on))))
+
+
+def set_reserved_sms(n):
+    """Size every later grid of the library for (SM count - n) SMs, leaving n SMs to NCCL's channel CTAs (data parallel:
+    set it to NCCL_MAX_CTAS before the step is captured).  Returns the previous reservation."""
+    return int(lib().b3d_set_reserved_sms(c_int(int(n))))

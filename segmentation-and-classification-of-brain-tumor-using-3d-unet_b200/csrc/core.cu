@@ -17,15 +17,20 @@ void b3d_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// SMs left free for someone else's resident CTAs (NCCL channel CTAs under data parallelism): every grid of this library is
+// sized from b3d_num_sms(), and the tensor-core kernels are persistent one-CTA-per-SM grids that cannot share an SM with an
+// NCCL CTA — a conv CTA that finds "its" SM taken waits for the whole collective to finish.
+std::atomic<int> g_b3d_reserved_sms{getenv("B3D_RESERVED_SMS") ? atoi(getenv("B3D_RESERVED_SMS")) : 0};
+
 int b3d_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
+  static const int sms = [] {
+    int dev = 0, n = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const int r = g_b3d_reserved_sms.load(std::memory_order_relaxed);
+  return r > 0 ? (sms - r > 8 ? sms - r : 8) : sms;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -75,6 +80,8 @@ const char* b3d_last_error_string() { return g_err; }
 int b3d_version() { return 100; }
 long long b3d_launch_count() { return g_b3d_launches.load(); }
 // 1: bit-reproducible forward / input gradients (single MMA issuer in the z-marching conv kernel); returns the old value
+// grids of every later launch use (SM count - n) SMs; returns the previous reservation.  Process-wide, atomic.
+int b3d_set_reserved_sms(int n) { return g_b3d_reserved_sms.exchange(n < 0 ? 0 : n); }
 int b3d_set_ordered_issue(int on) { return g_b3d_ordered_issue.exchange(on < 0 ? 0 : (on > 2 ? 2 : on)); }
 // 0 if the current device is sm_100 (B200); negative otherwise — callers must fail loudly, there is no fallback.
 int b3d_check_device() {
