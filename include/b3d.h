@@ -69,6 +69,12 @@ int b3d_conv_fprop_add(const void* x, long long ldx, const void* wpack, int w_ro
  * [Cout][Cin + Cout] = [mode-1 packed W | identity]; y may alias addend. */
 int b3d_conv1_add_mma(const void* x, long long ldx, const void* addend, long long ld_add, const void* wpack_aug, int w_rows,
                       void* y, long long ldy, int N, int D, int H, int W, int Cin, int Cout, int* err_flag, void* stream);
+/* Scratch the caller must pass as (ws, ws_bytes) to the calls above / below (the library allocates nothing; SURVEY section 8b
+ * "b3d_workspace_bytes_*").  conv_fprop: split-K partial slices, 0 = pass NULL (large problems never split). */
+size_t b3d_conv_fprop_workspace_bytes(int N, int D, int H, int W, int Cout);
+size_t b3d_convT2_dgrad_workspace_bytes(int N, int D, int H, int W, int Cin);
+size_t b3d_conv_wgrad_workspace_bytes(int Cin, int Cout, int ks);
+size_t b3d_convT2_wgrad_workspace_bytes(int Cin, int Cout);
 /* tuning hooks of the implicit-GEMM tile planner (0 = planner's choice); not used by the product path */
 int b3d_set_plan_override(int td, int th, int tw, int kc, int bn);
 const char* b3d_last_plan(void);

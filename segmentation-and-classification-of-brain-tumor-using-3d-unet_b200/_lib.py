@@ -26,6 +26,9 @@ def lib():
                 "libb3d.so not built (%s). Run `python __graft_entry__.py build`; there is no CPU/cuDNN fallback." % path)
         _LIB = ctypes.CDLL(path)
         _LIB.b3d_last_error_string.restype = ctypes.c_char_p
+        for fn in ("b3d_conv_fprop_workspace_bytes", "b3d_convT2_dgrad_workspace_bytes", "b3d_conv_wgrad_workspace_bytes",
+                   "b3d_convT2_wgrad_workspace_bytes"):
+            getattr(_LIB, fn).restype = ctypes.c_size_t
     return _LIB
 
 

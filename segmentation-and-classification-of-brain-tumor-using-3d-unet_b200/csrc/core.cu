@@ -83,6 +83,24 @@ long long b3d_launch_count() { return g_b3d_launches.load(); }
 // grids of every later launch use (SM count - n) SMs; returns the previous reservation.  Process-wide, atomic.
 int b3d_set_reserved_sms(int n) { return g_b3d_reserved_sms.exchange(n < 0 ? 0 : n); }
 int b3d_set_ordered_issue(int on) { return g_b3d_ordered_issue.exchange(on < 0 ? 0 : (on > 2 ? 2 : on)); }
+// ---- workspace sizes: the caller allocates every scratch buffer (nothing persistent lives in the library), these say how much ----
+// split-K partial slices of b3d_conv_fprop / b3d_conv_fprop_add: up to 16 fp32 slices [split][voxels][Cout]; only the small
+// (deep-level) problems ever split, so problems whose 16 slices would exceed 64 MB get none (0 = pass ws = NULL).
+size_t b3d_conv_fprop_workspace_bytes(int N, int D, int H, int W, int Cout) {
+  const size_t one = (size_t)N * D * H * W * Cout * 4;
+  return one * 16 <= ((size_t)1 << 26) ? one * 16 : 0;
+}
+// b3d_convT2_dgrad: the same policy on its [voxels][Cin] output (one slice is always required)
+size_t b3d_convT2_dgrad_workspace_bytes(int N, int D, int H, int W, int Cin) {
+  const size_t one = (size_t)N * D * H * W * Cin * 4;
+  return one * 16 <= ((size_t)1 << 26) ? one * 16 : one;
+}
+// b3d_conv_wgrad: the tap-major fp32 accumulator [ks^3][Cin][roundup16(Cout)] the flush kernels reduce into before the
+// transposing finalize writes the reference layout; b3d_convT2_wgrad: [8][Cin][Cout]
+size_t b3d_conv_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
+  return (size_t)ks * ks * ks * Cin * ((Cout + 15) / 16 * 16) * 4;
+}
+size_t b3d_convT2_wgrad_workspace_bytes(int Cin, int Cout) { return (size_t)8 * Cin * Cout * 4; }
 // 0 if the current device is sm_100 (B200); negative otherwise — callers must fail loudly, there is no fallback.
 int b3d_check_device() {
   int dev = 0, major = 0, minor = 0;

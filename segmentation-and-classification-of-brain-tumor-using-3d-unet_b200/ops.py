@@ -202,9 +202,8 @@ def conv_fprop(x, wpack, w_rows, cout, ks, bias=None, groups=0, stats_batch=Fals
     stats = None
     if groups:
         stats = zeros_scratch((1 if stats_batch else n, groups, 2), torch.float64, dev)
-    # split-K workspace: up to 16 fp32 partial slices [split][V][Cout]; only small (deep-level) problems ever split
-    one = n * d * h * w * cout * 4
-    ws_bytes = one * 16 if (one * 16 <= (1 << 26) and add is None) else 0
+    # split-K workspace (fp32 partial slices [split][V][Cout]): the library states how much it wants for this shape
+    ws_bytes = int(_L().b3d_conv_fprop_workspace_bytes(c_int(n), c_int(d), c_int(h), c_int(w), c_int(cout))) if add is None else 0
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
     with _prof("igemm", 2.0 * n * d * h * w * (cin if cin_real is None else cin_real) * cout * ks ** 3, "conv%d %dx%dx%dx%d %d->%d" % (ks, n, d, h, w, cin, cout)):
         check(_L().b3d_conv_fprop_add(ptr(x), c_ll(ld(x)), ptr(wpack), c_int(w_rows), ptr(bias), ptr(add),
@@ -258,8 +257,8 @@ def convT2_dgrad(dy, wpack, w_rows, cin, out=None):
     dev = dy.device
     if out is None:
         out = new_act(n, d, h, w, cin, dev)
-    one = n * d * h * w * cin
-    ws = torch.empty(one * 16 if one * 64 <= (1 << 26) else one, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(_L().b3d_convT2_dgrad_workspace_bytes(c_int(n), c_int(d), c_int(h), c_int(w), c_int(cin))) // 4,
+                     dtype=torch.float32, device=dev)
     with _prof("igemm", 2.0 * n * d * h * w * cin * cout * 8, "convT_dgrad %dx%dx%dx%d %d<-%d" % (n, d, h, w, cin, cout)):
         check(_L().b3d_convT2_dgrad(ptr(dy), c_ll(ld(dy)), ptr(wpack), c_int(w_rows), ptr(out), c_ll(ld(out)), c_int(n),
                                     c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(ws), c_sz(ws.numel() * 4),
@@ -382,7 +381,7 @@ def _conv_wgrad(x, dy, cin_real, cout, ks, dw=None, accumulate=False):
         accumulate = False
     cout_pad = roundup(cout, 16)
     assert dy.shape[-1] == cout and (cout_pad == cout or ld(dy) >= cout_pad), "dy must expose padded channels"
-    ws = torch.empty(ks ** 3 * cin * cout_pad, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(_L().b3d_conv_wgrad_workspace_bytes(c_int(cin), c_int(cout), c_int(ks))) // 4, dtype=torch.float32, device=dev)
     with _prof("wgrad", 2.0 * n * d * h * w * cin_real * cout * ks ** 3, "wgrad%d %dx%dx%dx%d %d,%d" % (ks, n, d, h, w, cin, cout)), \
             _prof_bw("wgrad_pw" if ks == 1 else "wgrad3_bytes", n * d * h * w * (cin + cout) * 2, "wgrad%d" % ks):
         check(_L().b3d_conv_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
@@ -404,7 +403,7 @@ def _convT2_wgrad(x, dy, cin, cout, dw=None, accumulate=False):
     if dw is None:
         dw = torch.empty((cin, cout, 2, 2, 2), dtype=torch.float32, device=dev)
         accumulate = False
-    ws = torch.empty(8 * cin * cout, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(_L().b3d_convT2_wgrad_workspace_bytes(c_int(cin), c_int(cout))) // 4, dtype=torch.float32, device=dev)
     with _prof("wgrad", 2.0 * n * d * h * w * cin * cout * 8, "wgradT %dx%dx%dx%d %d,%d" % (n, d, h, w, cin, cout)):
         check(_L().b3d_convT2_wgrad(ptr(x), c_ll(ld(x)), ptr(dy), c_ll(ld(dy)), ptr(dw), c_int(1 if accumulate else 0), c_int(n),
                                     c_int(d), c_int(h), c_int(w), c_int(cin), c_int(cout), ptr(ws), c_sz(ws.numel() * 4),

@@ -50,6 +50,29 @@ def test_error_channel_without_gpu(lib_path):
         assert len(lib.b3d_last_error_string()) > 0
 
 
+def test_workspace_queries_and_process_wide_knobs_are_host_only(lib_path):
+    """The caller owns every scratch buffer: the size queries are pure host arithmetic, and the process-wide
+    knobs (SM reservation for data-parallel runs, ordered issue) return the previous value — no device needed."""
+    lib = ctypes.CDLL(lib_path)
+    for fn in ("b3d_conv_fprop_workspace_bytes", "b3d_convT2_dgrad_workspace_bytes", "b3d_conv_wgrad_workspace_bytes",
+               "b3d_convT2_wgrad_workspace_bytes"):
+        getattr(lib, fn).restype = ctypes.c_size_t
+    # deep level of cfg 3 (2 x 8^3 voxels, 512 channels): 16 split-K slices of 2 MB; level 0 (2 x 128^3 x 32): never splits
+    assert lib.b3d_conv_fprop_workspace_bytes(2, 8, 8, 8, 512) == 16 * 2 * 512 * 512 * 4
+    assert lib.b3d_conv_fprop_workspace_bytes(2, 128, 128, 128, 32) == 0
+    # ConvTranspose dgrad always needs one fp32 slice of its output
+    assert lib.b3d_convT2_dgrad_workspace_bytes(2, 64, 64, 64, 64) == 2 * 64 ** 3 * 64 * 4
+    assert lib.b3d_convT2_dgrad_workspace_bytes(2, 4, 4, 4, 1024) == 16 * 2 * 64 * 1024 * 4
+    # weight-gradient accumulators: [taps][Cin][roundup16(Cout)] and [8][Cin][Cout] fp32
+    assert lib.b3d_conv_wgrad_workspace_bytes(32, 4, 1) == 32 * 16 * 4
+    assert lib.b3d_conv_wgrad_workspace_bytes(512, 1024, 3) == 27 * 512 * 1024 * 4
+    assert lib.b3d_convT2_wgrad_workspace_bytes(1024, 512) == 8 * 1024 * 512 * 4
+    old = lib.b3d_set_reserved_sms(8)
+    assert lib.b3d_set_reserved_sms(old) == 8
+    mode = lib.b3d_set_ordered_issue(2)
+    assert lib.b3d_set_ordered_issue(mode) == 2
+
+
 def test_sass_contains_blackwell_tensor_and_tma_ops(lib_path):
     """tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, TMA -> UTMALDG (B200_PROFILING.md table)."""
     out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
