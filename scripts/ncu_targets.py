@@ -1,5 +1,5 @@
 """A few launches of each kernel whose `ncu --set full` capture is committed under profiles/ (one target per invocation):
-    python scripts/ncu_targets.py zs | pwadd | dsloss | adamw | gnbwd | deep"""
+    python scripts/ncu_targets.py zs | pwadd | dsloss | adamw | gnbwd | deep | convT | convTd"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,6 +9,16 @@ from unet3d_b200 import ops
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 what = sys.argv[1]
+
+
+def b3d_plan():
+    import ctypes
+    from unet3d_b200 import _lib
+    f = _lib.lib().b3d_last_plan
+    f.restype = ctypes.c_char_p
+    return f().decode()
+
+
 bf = torch.bfloat16
 if what == "zs":        # 32 -> 32 3x3x3 conv @2x128^3 with GroupNorm statistics: zs_kernel<32,32>
     x = torch.randn(2, 128, 128, 128, 32, device=dev).to(bf)
@@ -58,5 +68,23 @@ elif what == "deep":    # weight-streaming deep-level conv: 3x3x3 1024 -> 512 @2
     for _ in range(4):
         flush.zero_()                      # weights come from HBM, as inside a real step
         ops.conv_fprop(x, wp, rows, 512, 3, groups=8)
+elif what == "convT":   # ConvTranspose3d(k2,s2) fprop 64 -> 32 @2x64^3 -> 2x128^3 (ups.12), pixel-shuffle epilogue into a concat slice
+    x = torch.randn(2, 64, 64, 64, 64, device=dev).to(bf)
+    w = torch.randn(64, 32, 2, 2, 2, device=dev) * 0.05
+    packs = ops.pack_weight_pair(w, True)
+    wp = packs[ops.PACK_CONVT_FPROP][0]
+    cat = torch.empty(2, 128, 128, 128, 64, device=dev, dtype=bf)
+    bias = torch.zeros(32, device=dev)
+    for _ in range(4):
+        ops.convT2_fprop(x, wp, bias, 32, out=cat[..., 32:])
+    print(b3d_plan())
+elif what == "convTd":  # its data gradient: 2x128^3x32 -> 2x64^3x64 (8 strided K-maps)
+    dy = torch.randn(2, 128, 128, 128, 32, device=dev).to(bf)
+    w = torch.randn(64, 32, 2, 2, 2, device=dev) * 0.05
+    packs = ops.pack_weight_pair(w, True)
+    wd, _, rows = packs[ops.PACK_CONVT_DGRAD]
+    for _ in range(4):
+        ops.convT2_dgrad(dy, wd, rows, 64)
+    print(b3d_plan())
 torch.cuda.synchronize()
 print("ok", what)
