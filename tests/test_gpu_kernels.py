@@ -532,3 +532,40 @@ def test_conv1_fused_addend(dims, cin, cout, alias):
         ops.conv_fprop(x, wp, rows, cout, 1, out=out, add=add)
         assert float(wide[..., :cout].abs().max()) == 0.0
     _close_bf16(out, ref)
+
+
+@pytest.mark.parametrize("reserved", [20, 100])
+def test_results_do_not_depend_on_the_grid_width(reserved):
+    """`b3d_set_reserved_sms` (data parallel: SMs left to NCCL's channel CTAs) only changes how the persistent grids split the
+    work: conv fprop (z-marching and implicit-GEMM paths), weight gradients and GroupNorm agree with the full-width launch
+    (same bf16 outputs up to the fp32 summation order of split-K / atomics) and with PyTorch."""
+    from unet3d_b200 import _lib
+    x = _bf(2, 16, 16, 32, 32, seed=71)
+    w = (_bf(64, 32, 3, 3, 3, seed=72).float() / (32 * 27) ** 0.5).to(BF).float()
+    wp, kp, rows = ops.pack_weight(w, ops.PACK_FPROP)
+    xd = _bf(2, 4, 4, 4, 256, seed=73)
+    wd = (_bf(256, 256, 3, 3, 3, seed=74).float() / (256 * 27) ** 0.5).to(BF).float()
+    wdp, _, rowsd = ops.pack_weight(wd, ops.PACK_FPROP)
+    dy = _bf(2, 16, 16, 32, 64, seed=75)
+    gam, bet = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV)
+
+    def run():
+        y, st = ops.conv_fprop(x, wp, rows, 64, 3, groups=8)
+        yd, _ = ops.conv_fprop(xd, wdp, rowsd, 256, 3, groups=8)
+        dw = ops.conv_wgrad(x, dy, 32, 64, 3)
+        a = ops.gn_apply(y, st, gam, bet, 8, True)
+        ops.wgrad_join()
+        torch.cuda.synchronize()
+        return y, st, yd, dw, a
+
+    full = run()
+    old = _lib.set_reserved_sms(reserved)
+    try:
+        part = run()
+    finally:
+        _lib.set_reserved_sms(old)
+    ref = _ndhwc(F.conv3d(_ncdhw(x), w, None, padding=1))
+    _close_bf16(part[0], ref)
+    for a, b in zip(full, part):
+        scale = max(a.float().abs().max().item(), 1e-6)
+        assert (a.float() - b.float()).abs().max().item() <= scale / 128, "grid width changed a result"
