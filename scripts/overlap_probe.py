@@ -66,6 +66,7 @@ def timed(fn, it=20):
     tot = 0.0
     for _ in range(it):
         ops.reset_scratch()
+        torch.cuda._sleep(int(0.002 * 1.9e9))   # ~2 ms spin: the host enqueues everything before the device gets there
         e0.record(); fn(); e1.record()
         torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
