@@ -1,5 +1,5 @@
 """A few launches of each kernel whose `ncu --set full` capture is committed under profiles/ (one target per invocation):
-    python scripts/ncu_targets.py zs | pwadd | dsloss | adamw | gnbwd | deep | convT | convTd"""
+    python scripts/ncu_targets.py zs | pwadd | dsloss | adamw | gnbwd | deep | convT | convTd | wgdeep"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -86,5 +86,11 @@ elif what == "convTd":  # its data gradient: 2x128^3x32 -> 2x64^3x64 (8 strided 
     for _ in range(4):
         ops.convT2_dgrad(dy, wd, rows, 64)
     print(b3d_plan())
+elif what == "wgdeep":  # bottleneck weight gradient: 3x3x3 1024 -> 1024 @2x4^3 (113 MB of fp32 dW): wgrad_kernel + finalize
+    x = torch.randn(2, 4, 4, 4, 1024, device=dev).to(bf)
+    dy = torch.randn(2, 4, 4, 4, 1024, device=dev).to(bf)
+    ops.WGRAD_SIDE = False
+    for _ in range(4):
+        ops.conv_wgrad(x, dy, 1024, 1024, 3)
 torch.cuda.synchronize()
 print("ok", what)

@@ -99,8 +99,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
-      tma_prefetch_desc(&P.tmX);
+    // The whole warp walks the schedule (uniform control flow).  In plane mode a plane is CI8 / CO8 boxes of one 16-byte channel
+    // chunk each (they sit at a padded pitch in shared memory): lane c issues the box of chunk c, so a plane costs one issue
+    // slot instead of 16-32 serial TMA issues on one thread — at the 4^3 / 8^3 levels (8 tiny planes per key) that serial
+    // issue, not the flush, bounded the kernel (ncu: 44 % of the stall samples in the accumulator-full wait of the flush warps).
+    {
+      if (lane == 0) tma_prefetch_desc(&P.tmX);
       uint32_t Q = 0, T = 0;  // running X-plane / dY-plane fill counters
       for (int item = item_beg; item < item_end; ++item) {
         const int key = item / P.items_per_key;
@@ -120,14 +124,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             const int z = z0 + s + zoff;
             const uint32_t fb = xfull0 + 8 * slot;
             if (z >= 0 && z < P.D) {
-              mbar_expect_tx(fb, P.x_tx_bytes);
+              if (lane == 0) mbar_expect_tx(fb, P.x_tx_bytes);
+              __syncwarp();
               if (P.plane_mode) {
-                for (int c8 = 0; c8 < P.CI8; ++c8)  // one box per chunk: chunks sit at the padded pitch XP
+                for (int c8 = lane; c8 < P.CI8; c8 += 32)  // one box per chunk: chunks sit at the padded pitch XP
                   tma_load_5d(sX + slot * P.x_slot_bytes + c8 * P.XP * 16, &P.tmX, fb, 0, -P.halo, y0 + yoff,
                               k.cib * P.CI8 + c8, n * P.D + z);
-              } else
+              } else if (lane == 0)
                 tma_load_5d(sX + slot * P.x_slot_bytes, &P.tmX, fb, 0, -P.halo, k.cib * P.CI8, y0 + yoff, n * P.D + z);
-            } else {
+            } else if (lane == 0) {
               mbar_arrive(fb);  // out-of-volume plane: nothing to load, the consumer skips it
             }
             ++Q;
@@ -137,12 +142,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
             const uint32_t slot = T & 1u, ph = (T >> 1) & 1u;
             mbar_wait(yempty0 + 8 * slot, ph ^ 1, P.err, 12);
             const uint32_t fb = yfull0 + 8 * slot;
-            mbar_expect_tx(fb, P.y_tx_bytes);
+            if (lane == 0) mbar_expect_tx(fb, P.y_tx_bytes);
+            __syncwarp();
             if (P.plane_mode) {
-              for (int c8 = 0; c8 < P.CO8; ++c8)
+              for (int c8 = lane; c8 < P.CO8; c8 += 32)
                 tma_load_5d(sY + slot * P.y_slot_bytes + c8 * P.YP * 16, &P.tmY[k.t8], fb, 0, 0, y0, k.cob * P.CO8 + c8,
                             n * P.D + z0 + t);
-            } else
+            } else if (lane == 0)
               tma_load_5d(sY + slot * P.y_slot_bytes, &P.tmY[k.t8], fb, 0, 0, k.cob * P.CO8, y0, n * P.D + z0 + t);
             ++T;
           }
@@ -334,49 +340,90 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 // Cin % 8 == 0) or 32 * ntaps per input channel (mode 1).  One input channel per block left 108-byte runs and ran the
 // 1024 x 1024 x 27 gradient at 2.3 TB/s.
 #define FIN_CIB 8
+// NT = taps (27 / 8 / 1): every index split below is a division by a compile-time constant when the block is full (8 input
+// channels) — the generic version spent ~100 instructions per element on runtime divisions and scalar 4-byte loads and was
+// issue-bound (2 TB/s on the 113 MB bottleneck gradient, profiles/overlap_probe_r2.txt context: 0.67 ms of the step is exposed
+// deep-level weight-gradient work).  Loads: one 16-byte load per lane, four dwacc rows per warp instruction, all in flight.
+template <int NT>
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ acc, float* __restrict__ dw, int mode,
-                                                             int ntaps, int Cin, int Cout, int Cin_pad, int Cout_pad,
-                                                             int accumulate) {
-  __shared__ float tile[FIN_CIB][27][33];
+                                                             int Cin, int Cout, int Cin_pad, int Cout_pad, int accumulate) {
+  __shared__ float tile[FIN_CIB][NT][33];
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * FIN_CIB;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nci = min(FIN_CIB, Cin - ci0), nco = min(32, Cout - co0);
-  // nine independent 128-byte row loads in flight per warp (one at a time left the large gradients latency bound)
-  const int nrows = nci * ntaps;
-  for (int r0 = w; r0 < nrows; r0 += 8 * 9) {
-    float v[9];
+  const int sub = lane >> 3, l4 = (lane & 7) * 4;      // row within a group of four, first of this lane's four columns
+  const bool col_ok = co0 + l4 < Cout_pad;             // Cout_pad % 16 == 0: a 16-byte chunk is inside the row or entirely outside
+  constexpr int ROWS_FULL = FIN_CIB * NT;
+  constexpr int U = (ROWS_FULL + 31) / 32;             // row groups per warp: 8 warps x 4 rows x U >= FIN_CIB * NT
+  if (nci == FIN_CIB) {
+    float4 v[U];
 #pragma unroll
-    for (int u = 0; u < 9; ++u) {
-      const int r = r0 + 8 * u;
-      const int tap = r / nci, cil = r - tap * nci;   // consecutive rows of one tap are adjacent in dwacc
-      v[u] = (r < nrows && lane < nco) ? __ldcs(acc + ((long long)tap * Cin_pad + ci0 + cil) * Cout_pad + co0 + lane) : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int r = (u * 8 + w) * 4 + sub;             // row r <-> (tap = r / 8, channel = r % 8): rows of one tap are adjacent
+      v[u] = (r < ROWS_FULL && col_ok)
+                 ? __ldcs(reinterpret_cast<const float4*>(acc + ((long long)(r >> 3) * Cin_pad + ci0 + (r & 7)) * Cout_pad + co0 + l4))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 9; ++u) {
-      const int r = r0 + 8 * u;
-      if (r < nrows) { const int tap = r / nci, cil = r - tap * nci; tile[cil][tap][lane] = v[u]; }
+    for (int u = 0; u < U; ++u) {
+      const int r = (u * 8 + w) * 4 + sub;
+      if (r < ROWS_FULL) {
+        float* t = &tile[r & 7][r >> 3][l4];
+        t[0] = v[u].x; t[1] = v[u].y; t[2] = v[u].z; t[3] = v[u].w;
+      }
+    }
+  } else {
+    const int nrows = nci * NT;
+    for (int r = w * 4 + sub; r < nrows; r += 32) {
+      const int tap = r / nci, cil = r - tap * nci;
+      const float4 q = col_ok ? __ldcs(reinterpret_cast<const float4*>(acc + ((long long)tap * Cin_pad + ci0 + cil) * Cout_pad + co0 + l4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* t = &tile[cil][tap][l4];
+      t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
     }
   }
   __syncthreads();
-  if (mode == 0) {
-    const int run = nci * ntaps;
-    for (int idx = threadIdx.x; idx < nco * run; idx += 256) {
-      const int col = idx / run, j = idx - col * run;
-      const int cil = j / ntaps, tap = j - cil * ntaps;
-      const long long o = ((long long)(co0 + col) * Cin + ci0) * ntaps + j;
-      const float v = tile[cil][tap][col];
-      dw[o] = accumulate ? dw[o] + v : v;
+  if (mode == 0) {   // dW[co][ci][tap]: per output channel one run of nci * NT consecutive floats
+    if (nci == FIN_CIB) {
+      constexpr int RUN = FIN_CIB * NT;
+      for (int idx = threadIdx.x; idx < nco * RUN; idx += 256) {
+        const int col = idx / RUN, j = idx - col * RUN;
+        const int cil = j / NT, tap = j - cil * NT;
+        const long long o = ((long long)(co0 + col) * Cin + ci0) * NT + j;
+        const float val = tile[cil][tap][col];
+        dw[o] = accumulate ? dw[o] + val : val;
+      }
+    } else {
+      const int run = nci * NT;
+      for (int idx = threadIdx.x; idx < nco * run; idx += 256) {
+        const int col = idx / run, j = idx - col * run;
+        const int cil = j / NT, tap = j - cil * NT;
+        const long long o = ((long long)(co0 + col) * Cin + ci0) * NT + j;
+        const float val = tile[cil][tap][col];
+        dw[o] = accumulate ? dw[o] + val : val;
+      }
     }
-  } else {
-    const int run = nco * ntaps;
+  } else {           // dWt[ci][co][t8]: per input channel one run of nco * NT consecutive floats
+    const int run = nco * NT;
     for (int idx = threadIdx.x; idx < nci * run; idx += 256) {
       const int cil = idx / run, j = idx - cil * run;
-      const int col = j / ntaps, tap = j - col * ntaps;
-      const long long o = ((long long)(ci0 + cil) * Cout + co0) * ntaps + j;
-      const float v = tile[cil][tap][col];
-      dw[o] = accumulate ? dw[o] + v : v;
+      const int col = j / NT, tap = j - col * NT;
+      const long long o = ((long long)(ci0 + cil) * Cout + co0) * NT + j;
+      const float val = tile[cil][tap][col];
+      dw[o] = accumulate ? dw[o] + val : val;
     }
   }
+}
+
+static cudaError_t launch_wgrad_finalize(const float* acc, float* dw, int mode, int ntaps, int Cin, int Cout, int Cin_pad,
+                                         int Cout_pad, int accumulate, cudaStream_t st) {
+  const dim3 grid((Cout + 31) / 32, (Cin + FIN_CIB - 1) / FIN_CIB);
+  if (ntaps == 27) wgrad_finalize_kernel<27><<<grid, 256, 0, st>>>(acc, dw, mode, Cin, Cout, Cin_pad, Cout_pad, accumulate);
+  else if (ntaps == 8) wgrad_finalize_kernel<8><<<grid, 256, 0, st>>>(acc, dw, mode, Cin, Cout, Cin_pad, Cout_pad, accumulate);
+  else if (ntaps == 1) wgrad_finalize_kernel<1><<<grid, 256, 0, st>>>(acc, dw, mode, Cin, Cout, Cin_pad, Cout_pad, accumulate);
+  else return cudaErrorInvalidValue;
+  ++g_b3d_launches;
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,8 +626,7 @@ int b3d_conv_wgrad(const void* x, long long ldx, const void* dy, long long lddy,
   if (rc < 0) return rc;
   if (rc > 0) rc = run_wgrad(x, ldx, Cin, &yv, 1, n, d, h, w, Cout, ks, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
-  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, (Cin_real + FIN_CIB - 1) / FIN_CIB), 256, 0, st>>>(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
-  B3D_CHECK_CUDA(cudaGetLastError());
+  B3D_CHECK_CUDA(launch_wgrad_finalize(ws, dw, 0, ntaps, Cin_real, Cout, Cin, Cout_pad, accumulate, st));
   return B3D_OK;
 }
 
@@ -604,8 +650,7 @@ int b3d_convT2_wgrad(const void* x, long long ldx, const void* dy, long long ldd
   if (rc < 0) return rc;
   if (rc > 0) rc = run_wgrad(x, ldx, Cin, yv, 8, N, D, H, W, Cout, 1, ws, Cin, Cout_pad, err_flag, st);
   if (rc) return rc;
-  wgrad_finalize_kernel<<<dim3((Cout + 31) / 32, (Cin + FIN_CIB - 1) / FIN_CIB), 256, 0, st>>>(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate); ++g_b3d_launches;
-  B3D_CHECK_CUDA(cudaGetLastError());
+  B3D_CHECK_CUDA(launch_wgrad_finalize(ws, dw, 1, 8, Cin, Cout, Cin, Cout_pad, accumulate, st));
   return B3D_OK;
 }
 
