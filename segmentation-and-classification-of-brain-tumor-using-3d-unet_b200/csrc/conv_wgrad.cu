@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __rest
   const int nci = min(FIN_CIB, Cin - ci0), nco = min(32, Cout - co0);
   const int sub = lane >> 3, l4 = (lane & 7) * 4;      // row within a group of four, first of this lane's four columns
   const bool col_ok = co0 + l4 < Cout_pad;             // Cout_pad % 16 == 0: a 16-byte chunk is inside the row or entirely outside
+  static_assert(FIN_CIB == 8, "the full-block path splits a row index with r >> 3 / r & 7");
   constexpr int ROWS_FULL = FIN_CIB * NT;
   constexpr int U = (ROWS_FULL + 31) / 32;             // row groups per warp: 8 warps x 4 rows x U >= FIN_CIB * NT
   if (nci == FIN_CIB) {
