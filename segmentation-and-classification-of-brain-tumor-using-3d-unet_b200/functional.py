@@ -293,8 +293,7 @@ def final_fwd(x, p, bufs, training, need_bwd):
                               update_running=training)
     w3 = p["final_conv.3.weight"]
     k = w3.shape[0]
-    hc = hbuf if hbuf.is_contiguous() else hbuf
-    logits = ops.final_head_fwd(hc, bn, p["final_conv.1.weight"], p["final_conv.1.bias"], w3.reshape(k, f2),
+    logits = ops.final_head_fwd(hbuf, bn, p["final_conv.1.weight"], p["final_conv.1.bias"], w3.reshape(k, f2),
                                 p["final_conv.3.bias"])
     saved = (x, hbuf, bn, training) if need_bwd else None
     return logits, saved

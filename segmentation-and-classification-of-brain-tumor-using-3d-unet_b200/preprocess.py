@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import c_int, c_ll, c_sz, c_vp, check, ptr, stream_ptr
+from ._lib import c_int, c_ll, c_sz, check, ptr, stream_ptr
 
 c_double, c_float, c_ull = ctypes.c_double, ctypes.c_float, ctypes.c_ulonglong
 TARGET = (128, 128, 128)
