@@ -287,15 +287,13 @@ def main():
             os.environ.setdefault("NCCL_MAX_CTAS", str(dp_reserved))
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
-    if dp_reserved > 0:
-        _lib.set_reserved_sms(dp_reserved)
     lib.b3d_launch_count.restype = ctypes.c_longlong
 
     torch.manual_seed(0)
     model = U.UNet3D(4, 4, features=feats, dropout_rate=0.2).to(dev)
     model.train()
     crit = U.DeepSupervisionLoss3D()
-    net = DataParallel(model, bucket_mb=float(os.environ.get("B3D_BUCKET_MB", "32"))) if world > 1 else model
+    net = DataParallel(model, bucket_mb=float(os.environ.get("B3D_BUCKET_MB", "32")), reserved_sms=dp_reserved) if world > 1 else model
     use_graph = not os.environ.get("B3D_NO_GRAPH")
     opt = U.make_adamw(model, lr=1e-4, weight_decay=1e-4, capturable=use_graph)
 

@@ -215,9 +215,15 @@ class _Null:
 class DataParallel(torch.nn.Module):
     """Wrap a UNet3D replica: forward is unchanged; backward all-reduces gradients bucket by bucket (see module doc)."""
 
-    def __init__(self, module, process_group=None, bucket_mb=32.0, broadcast_parameters=True):
+    def __init__(self, module, process_group=None, bucket_mb=32.0, broadcast_parameters=True, reserved_sms=0):
+        """reserved_sms > 0: size every grid of the library for (SM count - reserved_sms) SMs (`b3d_set_reserved_sms`, process-wide)
+        so NCCL's channel CTAs get SMs of their own; pair it with NCCL_MAX_CTAS=reserved_sms set before the communicator is
+        created.  Measured on 2 x B200 (profiles/dp_reserved_sms_r2.txt): no gain, so the default leaves it off."""
         super().__init__()
         self.module = module
+        if reserved_sms > 0:
+            from . import _lib
+            _lib.set_reserved_sms(reserved_sms)
         self.buckets = GradientBuckets(process_group, bucket_mb)
         module._on_grads = self.buckets.add
         module._on_backward_end = self.buckets.finish
